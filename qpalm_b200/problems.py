@@ -1,0 +1,211 @@
+"""Problem instances: the reference's own known-answer QPs and the synthetic BASELINE.json configs.
+
+Known-answer data is transcribed from the reference test-suite (file:line given per problem); the
+synthetic generators follow SURVEY.md 8(d) (distribution of /root/reference/simulations/randomQP.m:32-38)
+with numpy's PCG64 so that they are fast at the full BASELINE sizes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from .abi import CSC
+
+
+@dataclass
+class QP:
+    name: str
+    Q: CSC            # n x n, stype -1 (lower triangle)
+    A: CSC            # m x n
+    q: np.ndarray
+    bmin: np.ndarray
+    bmax: np.ndarray
+    c: float = 0.0
+    settings: dict = field(default_factory=dict)
+    expect_x: np.ndarray | None = None
+    expect_status: int | None = None
+    warm_x: np.ndarray | None = None
+    warm_y: np.ndarray | None = None
+
+    @property
+    def n(self):
+        return self.Q.ncol
+
+    @property
+    def m(self):
+        return self.A.nrow
+
+
+def _csc(nrow, ncol, p, i, x, stype=0):
+    return CSC(nrow, ncol, np.array(p), np.array(i), np.array(x, dtype=float), stype)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's known-answer problems
+# ---------------------------------------------------------------------------------------------
+def basic_qp(**settings) -> QP:
+    """tests/src/test_basic_qp.c:14-88 (n=4, m=5)."""
+    A = _csc(5, 4, [0, 1, 2, 3, 4], [3, 4, 0, 2], [-1.0, 0.025431136, -0.0001, 0.33066985])
+    Q = _csc(4, 4, [0, 1, 2, 3, 4], [0, 1, 2, 3], [1.0, 0.046415888, 0.0021544347, 0.0001], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, gamma_init=1e1, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("basic_qp", Q, A, np.array([-2.0146781, 2.9613971, 7.2865370, 7.8925204]),
+              -2 * np.ones(5), 2 * np.ones(5), 0.0, st,
+              expect_x=np.array([2.0, -63.801365, -3382.1109, -6.0483288]), expect_status=1)
+
+
+def nonconvex_qp(**settings) -> QP:
+    """tests/src/test_nonconvex_qp.c:14-125: basic_qp with Q[2][2] negated."""
+    p = basic_qp()
+    p.name = "nonconvex_qp"
+    p.Q.x[2] = -0.0021544347
+    p.settings = dict(eps_abs=1e-6, eps_rel=1e-6, nonconvex=1, scaling=0, max_rank_update_fraction=1.0, verbose=0)
+    p.settings.update(settings)
+    p.expect_x = None
+    return p
+
+
+def ls_qp(**settings) -> QP:
+    """tests/src/test_ls_qp.c:17-108 (all breakpoints of the line search are traversed)."""
+    A = _csc(2, 2, [0, 1, 2], [1, 0], [-1.0, 0.0001])
+    Q = _csc(2, 2, [0, 1, 2], [0, 1], [1.0, 0.0001], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, gamma_max=1e3, gamma_init=1e1, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("ls_qp", Q, A, np.array([2.5150105, 16.259589]), -2 * np.ones(2), 2 * np.ones(2), 0.0, st,
+              expect_x=np.array([-2.0, -2.0e4]), expect_status=1)
+
+
+def degen_hess_qp(**settings) -> QP:
+    """tests/src/test_degen_hess.c:17-104 (singular Hessian, one equality row)."""
+    A = _csc(4, 3, [0, 2, 4, 6], [0, 1, 0, 2, 0, 3], [1.0] * 6)
+    Q = _csc(3, 3, [0, 2, 4, 4], [0, 1, 0, 1], [1.0, -1.0, -1.0, 2.0], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("degen_hess", Q, A, np.array([-2.0, -6.0, 1.0]),
+              np.array([0.5, -10, -10, -10.0]), np.array([0.5, 10, 10, 10.0]), 0.0, st,
+              expect_x=np.array([5.5, 5.0, -10.0]), expect_status=1)
+
+
+def prim_inf_qp(**settings) -> QP:
+    """tests/src/test_prim_inf_qp.c:20-124."""
+    A = _csc(3, 2, [0, 2, 4], [0, 2, 1, 2], [1.0] * 4)
+    Q = _csc(2, 2, [0, 1, 2], [0, 1], [1.0, 1.5], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("prim_inf", Q, A, np.array([1.0, -2.0]), np.array([-5.0, -10, 16]), np.array([5.0, 10, 20]),
+              0.0, st, expect_status=-3)
+
+
+def dua_inf_qp(**settings) -> QP:
+    """tests/src/test_dua_inf_qp.c:19-134."""
+    A = _csc(3, 2, [0, 3, 6], [0, 1, 2, 0, 1, 2], [1.0] * 6)
+    Q = _csc(2, 2, [0, 1, 2], [0, 1], [1e-10, 1e-10], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("dua_inf", Q, A, np.array([1.0, -2.0]), np.array([-5.0, -10, -20]), np.array([5.0, 10, 20]),
+              0.0, st, expect_status=-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic BASELINE.json configurations
+# ---------------------------------------------------------------------------------------------
+def random_qp(n, m, dens_A=0.05, dens_M=0.007, seed=0, nonconvex_shift=0.0, name=None, **settings) -> QP:
+    """C1 / C5 style: A Bernoulli(dens_A) pattern with N(0,1) values; Q = M M' (lower stored,
+    diagonal always present) with M Bernoulli(dens_M) * N(0,1); q ~ N(0,1); bmin=-U, bmax=U."""
+    rng = np.random.default_rng(seed)
+    if dens_A >= 1.0:
+        A = CSC.from_dense(rng.standard_normal((m, n)))
+    else:
+        A = CSC.from_scipy(sp.random(m, n, density=dens_A, format="csc", random_state=rng,
+                                     data_rvs=rng.standard_normal))
+    if dens_M >= 1.0:
+        M = rng.standard_normal((n, n))
+        Qd = _gram(M)
+        if nonconvex_shift:
+            Qd[np.diag_indices(n)] -= nonconvex_shift
+        Q = CSC.from_dense(Qd, stype=-1)
+    else:
+        M = sp.random(n, n, density=dens_M, format="csc", random_state=rng, data_rvs=rng.standard_normal)
+        Qs = (M @ M.T).tocsc() + sp.eye(n, format="csc") * 0.0
+        Qs = Qs + sp.diags(np.zeros(n) - nonconvex_shift)
+        Ql = sp.tril(Qs, format="csc")
+        # keep the diagonal structurally present, as the survey generator does
+        Ql = (Ql + sp.diags(np.full(n, 1e-300))).tocsc()
+        Ql.data[np.abs(Ql.data) <= 1e-299] = 0.0
+        Ql.sort_indices()
+        Q = CSC(n, n, Ql.indptr, Ql.indices, Ql.data, -1)
+    q = rng.standard_normal(n)
+    bmin = -rng.random(m)
+    bmax = rng.random(m)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, verbose=0)
+    st.update(settings)
+    return QP(name or f"random_qp_n{n}_m{m}", Q, A, q, bmin, bmax, 0.0, st)
+
+
+def _gram(M: np.ndarray) -> np.ndarray:
+    """M M' in fp64; uses the GPU through torch when one is visible (data generation only)."""
+    try:
+        import torch
+        if torch.cuda.is_available() and M.shape[0] >= 2000:
+            t = torch.from_numpy(M).cuda()
+            return (t @ t.T).cpu().numpy()
+    except Exception:
+        pass
+    return M @ M.T
+
+
+def dense_qp(n, m, seed=0, **settings) -> QP:
+    """C3: both densities 1.0 (A and Q dense, still passed in CSC as the reference requires)."""
+    return random_qp(n, m, 1.0, 1.0, seed, name=f"dense_qp_n{n}_m{m}", **settings)
+
+
+def nonconvex_random_qp(n, m, seed=0, **settings) -> QP:
+    """C5: C1-style with Q <- Q - I and nonconvex=1."""
+    settings.setdefault("nonconvex", 1)
+    return random_qp(n, m, 0.05, 0.007, seed, nonconvex_shift=1.0, name=f"nonconvex_qp_n{n}", **settings)
+
+
+@dataclass
+class BatchQP:
+    """C4: one shared (Q, A) and nb instances differing in q, bmin, bmax."""
+    Q: CSC
+    A: CSC
+    q: np.ndarray      # nb x n
+    bmin: np.ndarray   # nb x m
+    bmax: np.ndarray   # nb x m
+    settings: dict
+
+    def instance(self, k) -> QP:
+        return QP(f"mpc_{k}", self.Q, self.A, self.q[k].copy(), self.bmin[k].copy(), self.bmax[k].copy(),
+                  0.0, dict(self.settings))
+
+
+def mpc_batch(nb, n=240, m0=709, seed=0, **settings) -> BatchQP:
+    """chain80w-sized sweep (simulations/chain80w/info.txt:20-22, simulations/chain80w.m:39-51,90-104):
+    Q 240x240 SPD dense, A = [A0 (709 x 240 dense); I_240]  =>  m = 949; instances are perturbations
+    of a base instance, one PRNG stream per instance (seed + k).  Settings follow chain80w.m:
+    scaling=2, proximal=FALSE, eps_abs_in=eps_rel_in=1, eps_prim_inf=eps_dual_inf=1e-6."""
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n)) / np.sqrt(n)
+    Qd = M @ M.T + 0.1 * np.eye(n)
+    A0 = rng.standard_normal((m0, n)) / np.sqrt(n)
+    Ad = np.vstack([A0, np.eye(n)])
+    m = m0 + n
+    xfeas = rng.standard_normal(n) * 0.5
+    base_q = rng.standard_normal(n)
+    q = np.empty((nb, n))
+    bmin = np.empty((nb, m))
+    bmax = np.empty((nb, m))
+    for k in range(nb):
+        r = np.random.default_rng(seed * 100003 + k + 1)
+        xk = xfeas + 0.1 * r.standard_normal(n)
+        ax = Ad @ xk
+        q[k] = base_q + 0.3 * r.standard_normal(n)
+        bmin[k] = ax - r.random(m) * 0.5
+        bmax[k] = ax + r.random(m) * 0.5
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, verbose=0, scaling=2, proximal=0, eps_abs_in=1.0, eps_rel_in=1.0,
+              eps_prim_inf=1e-6, eps_dual_inf=1e-6)
+    st.update(settings)
+    return BatchQP(CSC.from_dense(Qd, -1), CSC.from_dense(Ad, 0), q, bmin, bmax, st)
