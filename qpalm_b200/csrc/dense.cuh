@@ -1,0 +1,39 @@
+// dense.cuh -- dense FP64 building blocks of the Newton system (Q + A_J' Sigma_J A_J + I/gamma) d = -dphi:
+// DMMA (mma.sync m8n8k4 f64) NT-GEMM / SYRK, blocked right-looking Cholesky, blocked triangular
+// solves and the rank-k update/downdate.  All matrices are column-major with a leading dimension that
+// is a multiple of 128 (qb::kPanel); rows/columns beyond n are an identity pad.
+#pragma once
+#include "common.cuh"
+
+namespace qb {
+
+// C[M x N] = beta*C + alpha * A[M x K] * B[N x K]'      (A, B, C column-major; M, N % 128 == 0, K % 16 == 0)
+// lower_only: only tiles with block-row >= block-col are computed (SYRK / Cholesky trailing update).
+// C may alias A when N == 128 (in-place triangular solve of a panel against an inverted diagonal block).
+int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, const double *B, int ldb,
+             double *C, int ldc, double alpha, double beta, bool lower_only);
+
+// In-place blocked Cholesky of the lower triangle of L (npad x npad, ld).  invdiag receives the inverses
+// of the 128 x 128 diagonal blocks of the factor (npad/128 blocks, each 128 x 128 column-major, upper
+// part zero).  *info_dev (device int) is set to 1 + (first non-positive pivot column) on failure.
+int potrf_lower(cudaStream_t s, int npad, double *L, int ld, double *invdiag, int *info_dev);
+
+// Recompute invdiag from an existing factor (after an update/downdate sweep).
+int trtri_diag_blocks(cudaStream_t s, int npad, const double *L, int ld, double *invdiag);
+
+// v <- (L L')^{-1} v, v of length npad (pad entries must be 0).
+int chol_solve(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v);
+
+// L <- chol(L L' + sign * W W'), W npad x k (ldw), k <= 8 per call, destroys W.  coef/alpha are scratch
+// (coef: 2 * 32 * 18 doubles, alpha: 8 doubles).  *info_dev set to nonzero if a downdate loses
+// positive definiteness.
+int chol_updown(cudaStream_t s, int npad, double *L, int ld, double *W, int ldw, int k, int sign,
+                double *coef, int *info_dev);
+
+// L(lower) <- H(lower) + diag_add * I on the leading n x n block; pad block <- identity.
+int copy_lower_add_diag(cudaStream_t s, int n, int npad, const double *H, double *L, int ld, double diag_add);
+
+// out[i] = sum_j |S_ij| for the symmetric matrix given by its lower triangle (Gershgorin row sums)
+int sym_abs_rowsums(cudaStream_t s, int n, const double *H, int ld, double *out);
+
+}  // namespace qb

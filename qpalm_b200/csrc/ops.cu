@@ -1,0 +1,307 @@
+// ops.cu -- operator-level C ABI (include/qpalm_b200.h Part 2): host buffers in, host buffers out, each
+// call runs the same device kernels the solver uses.  These are the entry points the parity tests drive
+// "at identical iterates" against the oracle and the reference.
+#include "../../include/qpalm_b200.h"
+#include "engine.cuh"
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+using namespace qb;
+
+extern "C" int qpalm_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" const char *qpalm_b200_version(void) { return "qpalm_b200 0.1 (sm_100a)"; }
+
+namespace {
+struct EmptyCSC {
+  std::vector<long long> p, i; std::vector<double> x;
+  explicit EmptyCSC(size_t ncol) : p(ncol + 1, 0), i(1, 0), x(1, 0.0) {}
+};
+// engine from optional A (m x n) and optional Q (n x n); missing pieces are empty
+int make_engine(Engine **e, int n, int m, const solver_sparse *A, const solver_sparse *Q, bool need_LQ = false) {
+  EmptyCSC ea((size_t)n), eq((size_t)n);
+  std::vector<double> zn((size_t)n + 1, 0.0), zm((size_t)m + 1, 0.0);
+  const long long *Ap = A ? (const long long *)A->p : ea.p.data(), *Ai = A ? (const long long *)A->i : ea.i.data();
+  const double *Ax = A ? (const double *)A->x : ea.x.data();
+  const long long *Qp = Q ? (const long long *)Q->p : eq.p.data(), *Qi = Q ? (const long long *)Q->i : eq.i.data();
+  const double *Qx = Q ? (const double *)Q->x : eq.x.data();
+  return engine_create(e, n, m, Ap, Ai, Ax, Qp, Qi, Qx, zn.data(), zm.data(), zm.data(), need_LQ);
+}
+int up_int(Engine *e, int *dst, const c_int *src, int len) {
+  std::vector<int> t((size_t)len + 1);
+  for (int i = 0; i < len; i++) t[i] = (int)src[i];
+  QB_CUDA_TRY(cudaMemcpy(dst, t.data(), sizeof(int) * (size_t)len, cudaMemcpyHostToDevice));
+  (void)e;
+  return 0;
+}
+}  // namespace
+
+extern "C" int qpalm_b200_mat_vec(const solver_sparse *A, const c_float *x, c_float *y) {
+  Engine *e = nullptr;
+  const int nrow = (int)A->nrow, ncol = (int)A->ncol;
+  int rc;
+  if (A->stype != 0) {   // symmetric: only the lower triangle is read (stype -1)
+    if ((rc = make_engine(&e, ncol, 0, nullptr, A))) return rc;
+    upload(e, e->x, x, ncol); spmv_Q(e, e->x, e->Qx); rc = download(e, y, e->Qx, ncol);
+  } else {
+    if ((rc = make_engine(&e, ncol, nrow, A, nullptr))) return rc;
+    upload(e, e->x, x, ncol); spmv_A(e, e->x, e->Ax); rc = download(e, y, e->Ax, nrow);
+  }
+  engine_destroy(e);
+  return rc;
+}
+extern "C" int qpalm_b200_mat_tpose_vec(const solver_sparse *A, const c_float *x, c_float *y) {
+  if (A->stype != 0) return qpalm_b200_mat_vec(A, x, y);
+  Engine *e = nullptr;
+  const int nrow = (int)A->nrow, ncol = (int)A->ncol;
+  int rc;
+  if ((rc = make_engine(&e, ncol, nrow, A, nullptr))) return rc;
+  upload(e, e->y, x, nrow); spmv_At(e, e->y, e->Aty); rc = download(e, y, e->Aty, ncol);
+  engine_destroy(e);
+  return rc;
+}
+
+namespace qb { int ruiz_norms_public(Engine *e, double *colnorm_dev, double *rownorm_dev); }
+
+extern "C" int qpalm_b200_scale_data(solver_sparse *A, solver_sparse *Q, c_float *q, c_float *bmin, c_float *bmax,
+                                     c_int scaling_iters, c_float *D, c_float *E, c_float *c_out) {
+  const int n = (int)Q->ncol, m = (int)A->nrow;
+  Engine *e = nullptr;
+  int rc;
+  if ((rc = make_engine(&e, n, m, A, Q))) return rc;
+  upload(e, e->q, q, n); upload(e, e->bmin, bmin, m); upload(e, e->bmax, bmax, m);
+  double cc = 1.0;
+  rc = engine_ruiz_scale(e, (int)scaling_iters, &cc);
+  *c_out = cc;
+  rc |= download(e, D, e->D, n); rc |= download(e, E, e->E, m);
+  rc |= download(e, q, e->q, n); rc |= download(e, bmin, e->bmin, m); rc |= download(e, bmax, e->bmax, m);
+  // scaled matrix values back into the caller's CSC arrays
+  const long long *Ap = (const long long *)A->p, *Ai = (const long long *)A->i; double *Axv = (double *)A->x;
+  if (m > 0) {
+    if (e->A_dense) {
+      std::vector<double> At((size_t)n * m);
+      rc |= download(e, At.data(), e->At, n * m);
+      for (int j = 0; j < n; j++) for (long long k = Ap[j]; k < Ap[j + 1]; k++) Axv[k] = At[(size_t)j + (size_t)n * Ai[k]];
+    } else rc |= download(e, Axv, e->A_csc.x, (int)Ap[n]);
+  }
+  const long long *Qp = (const long long *)Q->p, *Qi = (const long long *)Q->i; double *Qxv = (double *)Q->x;
+  if (e->Q_dense) {
+    std::vector<double> Qd((size_t)n * n);
+    rc |= download(e, Qd.data(), e->Qd, n * n);
+    for (int j = 0; j < n; j++) for (long long k = Qp[j]; k < Qp[j + 1]; k++) if (Qi[k] >= j) Qxv[k] = Qd[(size_t)Qi[k] + (size_t)n * j];
+  } else {
+    std::vector<int> rp((size_t)n + 1);
+    std::vector<double> rx((size_t)e->Q_csr.nnz + 1);
+    QB_CUDA_TRY(cudaMemcpy(rp.data(), e->Q_csr.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+    rc |= download(e, rx.data(), e->Q_csr.x, (int)e->Q_csr.nnz);
+    std::vector<int> fill(rp.begin(), rp.end());
+    for (int j = 0; j < n; j++) for (long long k = Qp[j]; k < Qp[j + 1]; k++) { const long long i = Qi[k]; if (i < j) continue; Qxv[k] = rx[fill[i]++]; }
+  }
+  engine_destroy(e);
+  return rc;
+}
+
+extern "C" int qpalm_b200_mat_inf_norm_cols(const solver_sparse *M, c_float *E) {
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, (int)M->ncol, (int)M->nrow, M, nullptr))) return rc;
+  rc = ruiz_norms_public(e, e->tmp_n, e->tmp_m);
+  rc |= download(e, E, e->tmp_n, (int)M->ncol);
+  engine_destroy(e);
+  return rc;
+}
+extern "C" int qpalm_b200_mat_inf_norm_rows(const solver_sparse *M, c_float *E) {
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, (int)M->ncol, (int)M->nrow, M, nullptr))) return rc;
+  rc = ruiz_norms_public(e, e->tmp_n, e->tmp_m);
+  rc |= download(e, E, e->tmp_m, (int)M->nrow);
+  engine_destroy(e);
+  return rc;
+}
+
+extern "C" int qpalm_b200_residuals_active_set(const solver_sparse *A,
+        const c_float *Ax, const c_float *y, const c_float *sigma, const c_float *bmin, const c_float *bmax,
+        const c_float *Qx, const c_float *q, const c_float *x0, c_int proximal, c_float gamma,
+        const c_int *active_old,
+        c_float *Axys, c_float *z, c_float *pri_res, c_float *yh, c_float *Atyh, c_float *df, c_float *dphi,
+        c_int *active, c_int *nb_active, c_int *enter, c_int *nb_enter, c_int *leave, c_int *nb_leave) {
+  const int m = (int)A->nrow, n = (int)A->ncol;
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, n, m, A, nullptr))) return rc;
+  std::vector<double> sinv((size_t)m + 1);
+  for (int i = 0; i < m; i++) sinv[i] = 1.0 / sigma[i];
+  upload(e, e->Ax, Ax, m); upload(e, e->y, y, m); upload(e, e->sigma, sigma, m); upload(e, e->sigma_inv, sinv.data(), m);
+  upload(e, e->bmin, bmin, m); upload(e, e->bmax, bmax, m); upload(e, e->Qx, Qx, n); upload(e, e->q, q, n); upload(e, e->x0, x0, n);
+  cudaStreamSynchronize(e->stream);
+  up_int(e, e->active_old, active_old, m);
+  e->scaling = 0;
+  rc = step_residuals(e, proximal != 0, gamma, 0.0);
+  rc |= step_compact_lists(e);
+  rc |= sync_scalars(e);
+  *nb_active = (c_int)e->scal_host[S_NB_ACTIVE]; *nb_enter = (c_int)e->scal_host[S_NB_ENTER]; *nb_leave = (c_int)e->scal_host[S_NB_LEAVE];
+  rc |= download(e, Axys, e->Axys, m); rc |= download(e, z, e->z, m); rc |= download(e, pri_res, e->pri_res, m);
+  rc |= download(e, yh, e->yh, m); rc |= download(e, Atyh, e->Atyh, n); rc |= download(e, df, e->df, n); rc |= download(e, dphi, e->dphi, n);
+  rc |= download_int(e, (long long *)active, e->active, m);
+  rc |= download_int(e, (long long *)enter, e->enter, (int)*nb_enter);
+  rc |= download_int(e, (long long *)leave, e->leave, (int)*nb_leave);
+  engine_destroy(e);
+  return rc;
+}
+
+extern "C" int qpalm_b200_linesearch(c_int m_, c_float eta, c_float beta,
+        const c_float *Ad, const c_float *Ax, const c_float *y, const c_float *sigma,
+        const c_float *sqrt_sigma, const c_float *bmin, const c_float *bmax,
+        c_float *tau, c_float *sorted_s, c_int *sorted_idx, c_int *nL) {
+  const int m = (int)m_;
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, 1, m, nullptr, nullptr))) return rc;
+  upload(e, e->Ad, Ad, m); upload(e, e->Ax, Ax, m); upload(e, e->y, y, m); upload(e, e->sigma, sigma, m);
+  upload(e, e->sqrt_sigma, sqrt_sigma, m); upload(e, e->bmin, bmin, m); upload(e, e->bmax, bmax, m);
+  double eb[2] = {eta, beta};
+  QB_CUDA_TRY(cudaMemcpyAsync(e->scal_dev + S_ETA, eb, sizeof(double) * 2, cudaMemcpyHostToDevice, e->stream));
+  rc = linesearch_device(e, m, e->Ad, e->Ax, e->y, e->sigma, e->sqrt_sigma, e->bmin, e->bmax);
+  rc |= sync_scalars(e);
+  *tau = e->scal_host[S_TAU];
+  const int n_l = (int)e->scal_host[S_NL];
+  if (nL) *nL = n_l;
+  if (sorted_s && sorted_idx && n_l > 0) {
+    std::vector<unsigned long long> k((size_t)n_l); std::vector<unsigned int> v((size_t)n_l);
+    QB_CUDA_TRY(cudaMemcpy(k.data(), e->ls_key[0], sizeof(unsigned long long) * (size_t)n_l, cudaMemcpyDeviceToHost));
+    QB_CUDA_TRY(cudaMemcpy(v.data(), e->ls_val[0], sizeof(unsigned int) * (size_t)n_l, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_l; i++) { memcpy(&sorted_s[i], &k[i], 8); sorted_idx[i] = (c_int)v[i]; }
+  }
+  engine_destroy(e);
+  return rc;
+}
+
+extern "C" int qpalm_b200_newton_solve(const solver_sparse *Q, const solver_sparse *A, const c_float *sigma,
+        const c_int *active, c_float beta, const c_float *rhs, c_float *d, c_float *L_out) {
+  const int n = (int)Q->ncol, m = A ? (int)A->nrow : 0;
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, n, m, A, Q))) return rc;
+  int na = 0;
+  if (active && m > 0) {
+    std::vector<double> ss((size_t)m);
+    for (int i = 0; i < m; i++) { ss[i] = sqrt(sigma[i]); na += active[i] != 0; }
+    upload(e, e->sigma, sigma, m); upload(e, e->sqrt_sigma, ss.data(), m);
+    cudaStreamSynchronize(e->stream);
+    up_int(e, e->active, active, m);
+  }
+  std::vector<double> neg((size_t)n);
+  for (int i = 0; i < n; i++) neg[i] = -rhs[i];
+  upload(e, e->dphi, neg.data(), n);
+  rc = step_newton_refactor(e, active != nullptr && m > 0, true, beta, na);
+  rc |= step_newton_solve(e);
+  rc |= download(e, d, e->d, n);
+  if (L_out) {
+    std::vector<double> L((size_t)e->ld * e->npad);
+    QB_CUDA_TRY(cudaMemcpy(L.data(), e->L, sizeof(double) * L.size(), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) L_out[(size_t)i + (size_t)n * j] = (i >= j) ? L[(size_t)i + (size_t)e->ld * j] : 0.0;
+  }
+  int info = 0;
+  QB_CUDA_TRY(cudaMemcpy(&info, e->info_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  engine_destroy(e);
+  return rc ? rc : (info ? 1000 + info : 0);
+}
+
+extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *W, c_int update) {
+  const int n = (int)n_, k = (int)k_;
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, n, 0, nullptr, nullptr))) return rc;
+  const int ld = e->ld, npad = e->npad;
+  std::vector<double> Lp((size_t)ld * npad, 0.0);
+  for (int j = 0; j < npad; j++) for (int i = j; i < npad; i++)
+    Lp[(size_t)i + (size_t)ld * j] = (i < n && j < n) ? L[(size_t)i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
+  QB_CUDA_TRY(cudaMemcpy(e->L, Lp.data(), sizeof(double) * Lp.size(), cudaMemcpyHostToDevice));
+  QB_CUDA_TRY(cudaMemset(e->info_dev, 0, sizeof(int)));
+  rc = 0;
+  for (int off = 0; off < k && !rc; off += 8) {
+    const int kk = k - off < 8 ? k - off : 8;
+    std::vector<double> Wp((size_t)ld * 8, 0.0);
+    for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
+    QB_CUDA_TRY(cudaMemcpy(e->W, Wp.data(), sizeof(double) * Wp.size(), cudaMemcpyHostToDevice));
+    rc = chol_updown(e->stream, npad, e->L, ld, e->W, ld, kk, update ? +1 : -1, e->ud_coef, e->info_dev);
+  }
+  QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  QB_CUDA_TRY(cudaMemcpy(Lp.data(), e->L, sizeof(double) * Lp.size(), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) L[(size_t)i + (size_t)n * j] = (i >= j) ? Lp[(size_t)i + (size_t)ld * j] : 0.0;
+  int info = 0;
+  QB_CUDA_TRY(cudaMemcpy(&info, e->info_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  engine_destroy(e);
+  return rc ? rc : (info ? 1000 : 0);
+}
+
+extern "C" int qpalm_b200_lobpcg(const solver_sparse *Q, const c_float *x0, c_float *lambda_out, c_int *iters_out) {
+  Engine *e = nullptr; int rc;
+  if ((rc = make_engine(&e, (int)Q->ncol, 0, nullptr, Q))) return rc;
+  long long its = 0;
+  rc = lobpcg_device(e, x0, lambda_out, &its);
+  if (iters_out) *iters_out = its;
+  engine_destroy(e);
+  return rc;
+}
+
+// ---- micro-benchmarks for the FP64 tensor roofline ---------------------------------------------------
+__global__ void k_fill_rand(double *p, size_t len, unsigned long long seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long s = seed + i * 0x9E3779B97F4A7C15ull;
+    s ^= s >> 30; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 27; s *= 0x94D049BB133111EBull; s ^= s >> 31;
+    p[i] = (double)(s >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
+extern "C" int qpalm_b200_bench_dsyrk(c_int n_, c_int k_, c_int reps, double *ms_out) {
+  const int n = round_up((int)n_, 128), k = round_up((int)k_, 16);
+  double *W = nullptr, *C = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&W, sizeof(double) * (size_t)n * k));
+  QB_CUDA_TRY(cudaMalloc(&C, sizeof(double) * (size_t)n * n));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  QB_LAUNCH(k_fill_rand, 1024, 256, 0, s, W, (size_t)n * k, 1234ull);
+  QB_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)n * n, s));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  int rc = dgemm_nt(s, n, n, k, W, n, W, n, C, n, 1.0, 1.0, true);   // warm-up
+  cudaEventRecord(a, s);
+  for (int r = 0; r < reps && !rc; r++) rc = dgemm_nt(s, n, n, k, W, n, W, n, C, n, 1.0, 1.0, true);
+  cudaEventRecord(b, s);
+  QB_CUDA_TRY(cudaEventSynchronize(b));
+  float ms = 0; cudaEventElapsedTime(&ms, a, b);
+  *ms_out = ms / (reps > 0 ? reps : 1);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(W); cudaFree(C);
+  return rc;
+}
+__global__ void k_make_spd(int n, double *A) {   // A <- small random symmetric part + n on the diagonal (lower used)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i < n && i == j) A[(size_t)i + (size_t)n * j] += (double)n;
+}
+extern "C" int qpalm_b200_bench_potrf(c_int n_, c_int reps, double *ms_out) {
+  const int n = round_up((int)n_, 128);
+  double *A = nullptr, *L = nullptr, *X = nullptr; int *info = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&A, sizeof(double) * (size_t)n * n));
+  QB_CUDA_TRY(cudaMalloc(&L, sizeof(double) * (size_t)n * n));
+  QB_CUDA_TRY(cudaMalloc(&X, sizeof(double) * (size_t)n * 128));
+  QB_CUDA_TRY(cudaMalloc(&info, sizeof(int)));
+  QB_CUDA_TRY(cudaMemset(info, 0, sizeof(int)));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  QB_LAUNCH(k_fill_rand, 1024, 256, 0, s, A, (size_t)n * n, 99ull);
+  dim3 g(cdiv(n, 256), n);
+  QB_LAUNCH(k_make_spd, g, 256, 0, s, n, A);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float total = 0; int rc = 0;
+  for (int r = 0; r < reps + 1 && !rc; r++) {
+    QB_CUDA_TRY(cudaMemcpyAsync(L, A, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+    cudaEventRecord(a, s);
+    rc = potrf_lower(s, n, L, n, X, info);
+    cudaEventRecord(b, s);
+    QB_CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    if (r > 0) total += ms;
+  }
+  *ms_out = total / (reps > 0 ? reps : 1);
+  int hinfo = 0; cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(A); cudaFree(L); cudaFree(X); cudaFree(info);
+  return rc ? rc : hinfo;
+}
+
+// ---- batch API: implemented in batch.cu ---------------------------------------------------------------
