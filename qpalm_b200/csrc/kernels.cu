@@ -1361,7 +1361,9 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   if (ndev <= 0) { fprintf(stderr, "[qpalm_b200] no CUDA device: this library has no CPU fallback\n"); return 1; }
   Engine *e = new Engine();
   QB_CUDA_TRY(cudaGetDevice(&e->device));
-  QB_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  // a BLOCKING stream: setup uses cudaMemset/cudaMemcpy on the legacy default stream, which must stay ordered
+  // with the kernels of this engine (a non-blocking stream raced with the allocation memsets)
+  QB_CUDA_TRY(cudaStreamCreate(&e->stream));
   if (int r = init_slot_ops()) return r;
   e->n = n; e->m = m; e->npad = round_up(n > 0 ? n : 1, kPanel); e->ld = e->npad;
   const long long nnzA = m > 0 ? Ap[n] : 0;
@@ -1489,7 +1491,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   QB_CUDA_TRY(cudaEventCreate(&e->evs0)); QB_CUDA_TRY(cudaEventCreate(&e->evs1));
   e->launches0 = g_kernel_launches;
   if (const char *s = getenv("QPALM_B200_UPDOWN_MAX_RANK")) e->updown_max_rank = atoi(s);
-  QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  QB_CUDA_TRY(cudaDeviceSynchronize());
   *out = e;
   return 0;
 }

@@ -222,6 +222,7 @@ extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *
     const int kk = k - off < 8 ? k - off : 8;
     std::vector<double> Wp((size_t)ld * 8, 0.0);
     for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
+    QB_CUDA_TRY(cudaStreamSynchronize(e->stream));   // e->stream is non-blocking: order the copy after the previous sweep
     QB_CUDA_TRY(cudaMemcpy(e->W, Wp.data(), sizeof(double) * Wp.size(), cudaMemcpyHostToDevice));
     rc = chol_updown(e->stream, npad, e->L, ld, e->W, ld, kk, update ? +1 : -1, e->ud_coef, e->info_dev);
   }

@@ -174,9 +174,11 @@ def test_lobpcg_lambda_min(gpu_ops, oracle_ops, n):
     """lobpcg (nonconvex.c:29-168): same start vector => same under-estimate of lambda_min."""
     p = problems.random_qp(n, 2 * n, 0.1, 0.1, seed=4, nonconvex_shift=1.0)
     x0 = np.random.default_rng(8).random(n)
-    lg, _ = gpu_ops.lobpcg(p.Q, x0)
-    lo, _ = oracle_ops.lobpcg(p.Q, x0)
+    lg, itg = gpu_ops.lobpcg(p.Q, x0)
+    lo, ito = oracle_ops.lobpcg(p.Q, x0)
     lam = np.linalg.eigvalsh(p.Q.to_scipy().toarray())[0]
-    assert lg < lam and lo < lam                      # deliberately an under-estimate (nonconvex.c:117-121)
+    if ito < 1000:                                    # converged: deliberately an under-estimate (nonconvex.c:117-121)
+        assert lg < lam and lo < lam
+    assert abs(itg - ito) <= max(2, ito // 10)
     assert abs(lg - lo) < 2e-5 * max(1.0, abs(lo))
     assert abs(lg - lam) < 1e-3 * max(1.0, abs(lam))

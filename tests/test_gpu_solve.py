@@ -111,7 +111,8 @@ def test_basic_qp_limits_and_dual():
 def test_ls_qp(kw):
     p = problems.ls_qp()
     g = _check(p, **kw)
-    np.testing.assert_allclose(g.x, p.expect_x, atol=1e-5)
+    # the reference asserts 1e-5 absolute for its single (default scaling) variant; eps_rel = 1e-6 on |x| = 2e4
+    np.testing.assert_allclose(g.x, p.expect_x, atol=1e-5 if not kw else 0.05)
 
 
 @pytest.mark.parametrize("kw", VARIANTS)
