@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- QPALM hot path on B200: batched QP solves/sec and dense-QP time-to-solution.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+For N > 1 the driver launches one rank per GPU with torch.distributed.run; the ranks shard the
+independent QPs with no data-path collective (weak scaling: instances per GPU fixed).
+
+A *step* is one pass of the hot path over one batch of synthetic QPs:
+  workload "mpc_batch"  (BASELINE config 4): `--batch` chain80w-sized QPs (n=240, m=949, shared Q/A) per GPU,
+                        every QP solved from a cold start to eps 1e-6 through the batch entry point.
+  workload "dense"      (BASELINE config 3): one dense QP n=8000, m=16000 solved to eps 1e-6 (time-to-solution),
+                        reported as the `time_to_solution` block of the same JSON line at N = 1 and as the
+                        primary line when the batch kernels are not built.
+`value` is whole-job throughput with all inputs resident in HBM (CUDA-event time on the launching stream, max over
+ranks); `e2e` goes through the public C API with host buffers (setup/H2D + solve + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from qpalm_b200 import abi, problems  # noqa: E402
+from qpalm_b200.interface import Qpalm, load_library  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def product_lib():
+    lib = load_library("b200")
+    lib.qpalm_b200_get_stats.argtypes = [C.POINTER(abi.QPALMWorkspace), C.POINTER(abi.QPALMB200Stats)]
+    lib.qpalm_b200_bench_dmma_peak.argtypes = [C.POINTER(C.c_double)]
+    lib.qpalm_b200_bench_gemv.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.qpalm_b200_bench_dsyrk.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    lib.qpalm_b200_bench_potrf.argtypes = [abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    return lib
+
+
+def get_stats(lib, solver) -> abi.QPALMB200Stats:
+    st = abi.QPALMB200Stats()
+    lib.qpalm_b200_get_stats(solver._work, C.byref(st))
+    return st
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference / oracle CPU arm
+# ------------------------------------------------------------------------------------------------------
+def cpu_impl():
+    return ("reference", "reference") if os.path.exists(abi.REF_LIB) else ("oracle", "port")
+
+
+def cpu_threads():
+    return os.cpu_count() or 1
+
+
+def run_cpu_dense_sample(n, m, seed):
+    """Reference CPU path on a bounded sample of the dense workload: same generator, n x m reduced so that one
+    solve is ~10-30 s of CPU work.  Returns (seconds per solve, iterations)."""
+    impl, kind = cpu_impl()
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cpu_threads()))
+    p = problems.dense_qp(n, m, seed=seed)
+    s = Qpalm(impl)
+    for k, v in p.settings.items():
+        setattr(s.settings, k, v)
+    s.set_data(p.Q, p.A, p.q, p.bmin, p.bmax)
+    t0 = time.perf_counter()
+    s._allocate_work()
+    s._solve()
+    dt = time.perf_counter() - t0
+    r = s.result()
+    s.cleanup()
+    return dt, r, kind
+
+
+def run_cpu_batch_sample(b, count):
+    """Reference CPU path on `count` instances of the batch, one process per host core over disjoint ranges
+    (QPALM is single-threaded).  Returns solves/sec."""
+    import multiprocessing as mp
+    impl, kind = cpu_impl()
+    cores = min(cpu_threads(), count)
+    chunks = [list(range(k, count, cores)) for k in range(cores)]
+    global _CPU_BATCH
+    _CPU_BATCH = b          # inherited by the forked workers (ctypes-backed matrices cannot be pickled)
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_batch_worker, [(impl, ch) for ch in chunks])
+    dt = time.perf_counter() - t0
+    iters = [i for r in res for i in r]
+    return count / dt, cores, kind, iters
+
+
+_CPU_BATCH = None
+
+
+def _cpu_batch_worker(arg):
+    impl, idx = arg
+    b = _CPU_BATCH
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from qpalm_b200.interface import solve_qp
+    out = []
+    for k in idx:
+        q = b.instance(k)
+        r = solve_qp(impl, q.Q, q.A, q.q, q.bmin, q.bmax, **q.settings)
+        out.append(r.iter)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# dense workload (BASELINE config 3)
+# ------------------------------------------------------------------------------------------------------
+def bench_dense(args, lib, steps, warmup, sample_clocks=True):
+    import torch
+    n, m = args.n, args.m
+    p = problems.dense_qp(n, m, seed=args.seed)
+    h2d = 8 * (p.A.x.size + p.Q.x.size + n + 2 * m)
+    d2h = 8 * (n + m)
+    s = Qpalm("b200")
+    for k, v in p.settings.items():
+        setattr(s.settings, k, v)
+    s.set_data(p.Q, p.A, p.q, p.bmin, p.bmax)
+    t0 = time.perf_counter()
+    assert s._allocate_work(), "qpalm_setup failed"
+    setup_s = time.perf_counter() - t0
+    for _ in range(warmup):
+        s._solve()
+    st0 = get_stats(lib, s)
+    sampler = ClockSampler(torch.cuda.current_device())
+    if sample_clocks:
+        sampler.start()
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        s._solve()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sample_clocks else None
+    st1 = get_stats(lib, s)
+    res = s.result()
+    dev_ms = st1.device_ms_total - st0.device_ms_total
+    out = dict(
+        ms_per_solve=dev_ms / steps, status=res.status, iter=res.iter, iter_out=res.iter_out, setup_s=setup_s,
+        launches=int(st1.kernel_launches - st0.kernel_launches),
+        refactorizations=int(st1.refactorizations - st0.refactorizations) // steps,
+        refactor_active_avg=(st1.refactor_active_sum - st0.refactor_active_sum) / max(1, st1.refactorizations - st0.refactorizations),
+        updown_sweeps=int(st1.updown_calls - st0.updown_calls) // steps,
+        ms_factor=(st1.device_ms_factor - st0.device_ms_factor) / steps,
+        ms_updown=(st1.device_ms_updown - st0.device_ms_updown) / steps,
+        dense_flops=(st1.dense_flops - st0.dense_flops) / steps, alg_bytes=(st1.algorithmic_bytes - st0.algorithmic_bytes) / steps,
+        clocks=clocks, h2d=h2d, d2h=d2h, x=res.x, y=res.y, objective=res.objective)
+    s.cleanup()
+    # e2e: setup (H2D + Ruiz) + solve + solution read-back through the public API, host buffers
+    e2e = []
+    for _ in range(max(1, min(steps, 2))):
+        t0 = time.perf_counter()
+        s2 = Qpalm("b200")
+        for k, v in p.settings.items():
+            setattr(s2.settings, k, v)
+        s2.set_data(p.Q, p.A, p.q, p.bmin, p.bmax)
+        s2._allocate_work()
+        s2._solve()
+        r2 = s2.result()
+        e2e.append(time.perf_counter() - t0)
+        s2.cleanup()
+        assert r2.status_val == res.status_val
+    out["e2e_s"] = float(np.mean(e2e))
+    return out, p
+
+
+def tensor_roofline(lib, n, k_avg, dense):
+    """Dominant kernel of the dense workload: k_dgemm_nt (FP64 DMMA).  achieved = algorithmic flops of the
+    refactorisations (n^2 |J| SYRK + n^3/3 Cholesky) / their CUDA-event time inside the timed solves."""
+    peak = C.c_double(0)
+    lib.qpalm_b200_bench_dmma_peak(C.byref(peak))
+    flops = dense["refactorizations"] * (float(n) * n * k_avg + float(n) ** 3 / 3.0)
+    ach = flops / max(dense["ms_factor"], 1e-9) / 1e9     # TFLOP/s
+    ms = C.c_double(0)
+    lib.qpalm_b200_bench_dsyrk(n, max(16, int(k_avg)), 3, C.byref(ms))
+    syrk_tf = float(n) * n * max(16, int(k_avg)) / max(ms.value, 1e-9) / 1e9
+    lib.qpalm_b200_bench_potrf(n, 2, C.byref(ms))
+    potrf_tf = float(n) ** 3 / 3 / max(ms.value, 1e-9) / 1e9
+    return {"bound": "tensor", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / max(peak.value, 1e-9),
+            "traffic": None, "kernel": "k_dgemm_nt (FP64 DMMA SYRK + Cholesky trailing updates)",
+            "peak_source": "in-repo mma.sync.m8n8k4.f64 issue-rate microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
+            "syrk_alone_tflops": syrk_tf, "potrf_alone_tflops": potrf_tf}
+
+
+def hbm_roofline(lib, n, m):
+    hbm, src = measured_peaks()
+    a, b = C.c_double(0), C.c_double(0)
+    lib.qpalm_b200_bench_gemv(n, m, 20, C.byref(a), C.byref(b))
+    bytes_ = 8.0 * n * m
+    return {"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": src,
+            "A_times_x": {"achieved": bytes_ / (a.value * 1e-3) / 1e9, "frac": bytes_ / (a.value * 1e-3) / 1e9 / hbm},
+            "At_times_y": {"achieved": bytes_ / (b.value * 1e-3) / 1e9, "frac": bytes_ / (b.value * 1e-3) / 1e9 / hbm}}
+
+
+# ------------------------------------------------------------------------------------------------------
+# batched MPC workload (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------------
+def bench_batch(args, steps, warmup, rank, world):
+    import torch
+    from qpalm_b200 import batch as qb
+    nb = args.batch
+    b = problems.mpc_batch(nb, seed=args.seed + 1000 * rank)     # each rank owns a disjoint set of instances
+    h = qb.Batch(b.Q, b.A, b.settings, nb)
+    assert h.ok, "batch setup failed"
+    h.upload(b.q, b.bmin, b.bmax)
+    for _ in range(warmup):
+        h.solve_resident(nb)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    dev_ms = 0.0
+    for _ in range(steps):
+        dev_ms += h.solve_resident(nb)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    x, y, infos = h.download(nb)
+    # e2e: host buffers in, host results out, every step
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        xe, ye, ie = h.solve(b.q, b.bmin, b.bmax)
+    e2e_s = (time.perf_counter() - t0) / steps
+    launches = h.last_launches() if hasattr(h, "last_launches") else None
+    h.cleanup()
+    return dict(dev_ms=dev_ms, e2e_s=e2e_s, clocks=clocks, infos=infos, x=x, y=y, b=b, launches=launches,
+                h2d=8 * (b.q.size + b.bmin.size + b.bmax.size), d2h=8 * (x.size + y.size))
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "dense", "mpc_batch"])
+    ap.add_argument("--n", type=int, default=8000)
+    ap.add_argument("--m", type=int, default=16000)
+    ap.add_argument("--batch", type=int, default=512, help="instances per GPU (4096 / 8)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-n", type=int, default=1600, help="dense CPU sample size (m = 2n)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch CPU sample size (0: one instance per host core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense time-to-solution block")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
+
+    # ---------------- reference arm: the reference's CPU implementation, bounded sample ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        workload = args.workload
+        if workload == "auto":
+            workload = "mpc_batch"
+        impl, kind = cpu_impl()
+        if workload == "dense":
+            vals = []
+            for _ in range(steps):
+                dt, r, kind = run_cpu_dense_sample(args.cpu_n, 2 * args.cpu_n, args.seed)
+                vals.append(dt)
+            v = 1.0 / float(np.mean(vals))
+            sample = f"same generator at n={args.cpu_n}, m={2 * args.cpu_n} (setup+solve), {cpu_threads()} BLAS threads"
+            cfg = {"workload": f"dense random convex QP n={args.n} m={args.m} eps 1e-6", "sample": sample}
+            line = {"metric": "qp_solves_per_sec", "value": v, "unit": "solves/s", "ms_per_step": 1e3 / v}
+            cores = cpu_threads()
+        else:
+            b = problems.mpc_batch(args.batch, seed=args.seed)
+            count = args.cpu_batch or min(args.batch, 2 * cpu_threads())
+            for _ in range(max(0, args.warmup > 0)):
+                run_cpu_batch_sample(b, min(count, cpu_threads()))
+            vals = []
+            for _ in range(steps):
+                v, cores, kind, _ = run_cpu_batch_sample(b, count)
+                vals.append(v)
+            v = float(np.mean(vals))
+            sample = f"{count} of the {args.batch} instances per step, one single-threaded reference process per host core ({cores})"
+            cfg = {"workload": f"batched MPC sweep: {args.batch} chain80w-sized QPs (n=240, m=949) per GPU, eps 1e-6", "sample": sample}
+            line = {"metric": "qp_solves_per_sec", "value": v, "unit": "solves/s", "ms_per_step": 1e3 * count / v}
+        line.update({"impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "higher_is_better": True,
+                     "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                     "cpu_baseline": {"value": line["value"], "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample},
+                     "e2e": {"value": line["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line))
+        return
+
+    # ---------------- product arm ----------------
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = product_lib()
+    from qpalm_b200 import batch as qb
+    workload = args.workload
+    if workload == "auto":
+        workload = "mpc_batch" if qb.available() else "dense"
+
+    line = {"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic"}
+    if workload == "mpc_batch":
+        r = bench_batch(args, steps, warmup, rank, world)
+        t = torch.tensor([r["dev_ms"], r["e2e_s"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        total = args.batch * world
+        solved = sum(1 for i in r["infos"] if i["status_val"] == 1)
+        line.update({"metric": "qp_solves_per_sec", "unit": "solves/s", "value": total * steps / (dev_ms * 1e-3),
+                     "ms_per_step": dev_ms / steps,
+                     "config": {"workload": f"batched MPC sweep: {args.batch} chain80w-sized QPs (n=240, m=949, shared Q/A) per GPU, "
+                                            f"cold start, eps 1e-6; {total} QPs in flight over {world} GPU(s)",
+                                "batch_per_gpu": args.batch, "l2": "working set (per-instance factors) larger than L2",
+                                "solved": f"{solved}/{args.batch} on rank 0"},
+                     "e2e": {"value": total / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                     "clocks": r["clocks"], "gpu_launches": r["launches"]})
+        if rank == 0:
+            hbm, src = measured_peaks()
+            iters = float(np.mean([i["iter"] for i in r["infos"]]))
+            line["config"]["mean_iterations"] = iters
+            if not args.no_cpu:
+                b = r["b"]
+                count = args.cpu_batch or min(args.batch, cpu_threads())
+                v, cores, kind, cpu_iters = run_cpu_batch_sample(b, count)
+                line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": kind,
+                                        "sample": f"first {count} instances of rank 0's batch, one single-threaded reference process per core"}
+                line["config"]["cpu_mean_iterations"] = float(np.mean(cpu_iters))
+    else:
+        dense, p = bench_dense(args, lib, steps, warmup)
+        dev_ms = dense["ms_per_solve"]
+        line.update({"metric": "qp_solves_per_sec", "unit": "solves/s", "value": world * 1e3 / dev_ms, "ms_per_step": dev_ms,
+                     "config": {"workload": f"dense random convex QP n={args.n} m={args.m} eps 1e-6 (replica per GPU)",
+                                "l2": "inputs larger than L2 (A' is %.2f GB)" % (8.0 * args.n * args.m / 1e9),
+                                "status": dense["status"], "iter": dense["iter"], "iter_out": dense["iter_out"]},
+                     "e2e": {"value": world / dense["e2e_s"], "unit": "solves/s", "h2d_bytes_per_step": dense["h2d"], "d2h_bytes_per_step": dense["d2h"]},
+                     "clocks": dense["clocks"], "gpu_launches": dense["launches"] // steps})
+        if rank == 0:
+            line["roofline"] = tensor_roofline(lib, args.n, dense["refactor_active_avg"], dense)
+            line["roofline_hbm"] = hbm_roofline(lib, args.n, args.m)
+            line["time_to_solution"] = {"seconds": dev_ms * 1e-3, "e2e_seconds": dense["e2e_s"], "setup_seconds": dense["setup_s"],
+                                        "refactorizations": dense["refactorizations"], "updown_sweeps": dense["updown_sweeps"],
+                                        "ms_in_refactorizations": dense["ms_factor"], "ms_in_updown": dense["ms_updown"]}
+            if not args.no_cpu:
+                dt, rr, kind = run_cpu_dense_sample(args.cpu_n, 2 * args.cpu_n, args.seed)
+                line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "solves/s", "cores": cpu_threads(), "kind": kind,
+                                        "sample": f"same generator at n={args.cpu_n}, m={2 * args.cpu_n} (setup+solve {dt:.2f} s, "
+                                                  f"{rr.iter} iterations); Newton-system flops scale ~ (n/{args.cpu_n})^3"}
+    # the dense time-to-solution block rides along on the batch line at N = 1
+    if workload == "mpc_batch" and world == 1 and not args.no_dense:
+        dense, p = bench_dense(args, lib, 1, 1, sample_clocks=False)
+        line["time_to_solution"] = {"workload": f"dense random convex QP n={args.n} m={args.m} eps 1e-6",
+                                    "seconds": dense["ms_per_solve"] * 1e-3, "e2e_seconds": dense["e2e_s"], "setup_seconds": dense["setup_s"],
+                                    "status": dense["status"], "iter": dense["iter"], "iter_out": dense["iter_out"],
+                                    "refactorizations": dense["refactorizations"], "ms_in_refactorizations": dense["ms_factor"]}
+        line["roofline_tensor"] = tensor_roofline(lib, args.n, dense["refactor_active_avg"], dense)
+        line["roofline_hbm"] = hbm_roofline(lib, args.n, args.m)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -263,6 +263,10 @@ int qpalm_b200_lobpcg(const solver_sparse *Q, const c_float *x0, c_float *lambda
  * C(n x n lower) = W W' with W n x k; returns the average ms per call over `reps` calls. */
 int qpalm_b200_bench_dsyrk(c_int n, c_int k, c_int reps, double *ms_out);
 int qpalm_b200_bench_potrf(c_int n, c_int reps, double *ms_out);
+/* FP64 tensor-pipe (DMMA) issue-rate peak in TFLOP/s: register-resident mma.sync chains, no memory traffic. */
+int qpalm_b200_bench_dmma_peak(double *tflops_out);
+/* dense matrix-vector kernels at the solver's shapes (At is n x m): ms per A*x (column dots) and per A'*y (row sums) */
+int qpalm_b200_bench_gemv(c_int n, c_int m, c_int reps, double *ms_cols_out, double *ms_rows_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Part 3 -- batch entry point (additive).  `nb` QPs sharing Q, A (values and pattern) and settings

@@ -306,3 +306,76 @@ extern "C" int qpalm_b200_bench_potrf(c_int n_, c_int reps, double *ms_out) {
 }
 
 // ---- batch API: implemented in batch.cu ---------------------------------------------------------------
+
+// FP64 tensor-pipe issue-rate peak: register-resident mma.sync m8n8k4 chains, no memory traffic.
+// MEASURED_PEAKS.json has no FP64 entry, so bench.py uses this as the denominator of the tensor roofline.
+__global__ void __launch_bounds__(256) k_dmma_peak(int iters, double *sink) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i * 1e-9; }
+  double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(acc[i][0]), "+d"(acc[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+extern "C" int qpalm_b200_bench_dmma_peak(double *tflops_out) {
+  double *sink = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&sink, 8));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 4096, grid = 148 * 8;
+  QB_LAUNCH(k_dmma_peak, grid, 256, 0, s, 64, sink);
+  double best = 0;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(a, s);
+    QB_LAUNCH(k_dmma_peak, grid, 256, 0, s, iters, sink);
+    cudaEventRecord(b, s);
+    QB_CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    const double flops = (double)grid * 8 /*warps*/ * iters * 16.0 * 512.0;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  *tflops_out = best;
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(sink);
+  return 0;
+}
+
+// HBM roofline probes for the matrix-vector kernels: dense At (n x m) products at the solver's shapes.
+extern "C" int qpalm_b200_bench_gemv(c_int n_, c_int m_, c_int reps, double *ms_cols_out, double *ms_rows_out) {
+  const int n = (int)n_, m = (int)m_;
+  Engine e;   // minimal engine: only what the two dense kernels need
+  QB_CUDA_TRY(cudaStreamCreate(&e.stream));
+  e.n = n; e.m = m; e.A_dense = true;
+  QB_CUDA_TRY(cudaMalloc(&e.At, sizeof(double) * (size_t)n * m));
+  QB_CUDA_TRY(cudaMalloc(&e.x, sizeof(double) * n)); QB_CUDA_TRY(cudaMalloc(&e.y, sizeof(double) * m));
+  QB_CUDA_TRY(cudaMalloc(&e.Ax, sizeof(double) * m)); QB_CUDA_TRY(cudaMalloc(&e.Aty, sizeof(double) * n));
+  const int rowctas = cdiv(n, 128); int splits = cdiv(2048, rowctas); splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
+  e.gemv_splits = splits;
+  QB_CUDA_TRY(cudaMalloc(&e.gemv_partials, sizeof(double) * (size_t)splits * n));
+  QB_LAUNCH(k_fill_rand, 2048, 256, 0, e.stream, e.At, (size_t)n * m, 5ull);
+  QB_LAUNCH(k_fill_rand, 64, 256, 0, e.stream, e.x, (size_t)n, 6ull);
+  QB_LAUNCH(k_fill_rand, 64, 256, 0, e.stream, e.y, (size_t)m, 7ull);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  spmv_A(&e, e.x, e.Ax); spmv_At(&e, e.y, e.Aty);
+  float ms = 0;
+  cudaEventRecord(a, e.stream);
+  for (int r = 0; r < reps; r++) spmv_A(&e, e.x, e.Ax);
+  cudaEventRecord(b, e.stream); QB_CUDA_TRY(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms, a, b);
+  *ms_cols_out = ms / reps;
+  cudaEventRecord(a, e.stream);
+  for (int r = 0; r < reps; r++) spmv_At(&e, e.y, e.Aty);
+  cudaEventRecord(b, e.stream); QB_CUDA_TRY(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms, a, b);
+  *ms_rows_out = ms / reps;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(e.At); cudaFree(e.x); cudaFree(e.y); cudaFree(e.Ax); cudaFree(e.Aty); cudaFree(e.gemv_partials);
+  cudaStreamDestroy(e.stream);
+  return 0;
+}
