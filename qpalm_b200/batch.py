@@ -24,6 +24,8 @@ def _lib():
         lib.qpalm_b200_batch_solve_resident.restype = C.c_int
         lib.qpalm_b200_batch_download.argtypes = [C.c_void_p, abi.c_int, c_float_p, c_float_p, C.POINTER(QPALMInfo)]
         lib.qpalm_b200_batch_download.restype = C.c_int
+        lib.qpalm_b200_batch_last_launches.argtypes = [C.c_void_p]
+        lib.qpalm_b200_batch_last_launches.restype = C.c_longlong
         lib.qpalm_b200_batch_cleanup.argtypes = [C.c_void_p]
         lib.qpalm_b200_batch_cleanup.restype = None
         lib._batch_typed = True
@@ -85,6 +87,9 @@ class Batch:
         if rc:
             raise RuntimeError(f"batch_download failed: {rc}")
         return x, y, _infos(info, nb)
+
+    def last_launches(self):
+        return int(self.lib.qpalm_b200_batch_last_launches(self.h))
 
     def cleanup(self):
         if self.h:

@@ -323,7 +323,9 @@ struct Pending { int kind; };   // 0 none, 1 factor, 2 updown
 static void collect(Engine *e, Pending &p) {
   if (!p.kind) return;
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, e->evs0, e->evs1) == cudaSuccess) { if (p.kind == 1) e->ms_factor += ms; else e->ms_updown += ms; }
+  if (cudaEventElapsedTime(&ms, e->evs0, e->evs1) == cudaSuccess) {
+    if (p.kind == 1) { e->ms_factor += ms; e->last_refactor_ms = ms; } else e->ms_updown += ms;
+  }
   p.kind = 0;
 }
 
@@ -376,6 +378,17 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
   }
 }
 
+// Refactor-vs-update cost model: the rank-k sweep is a chain of npad/32 dependent panel steps
+// (~30 us + ~12 us per rank each, measured on B200), a refactorisation is DMMA-bound; the update path is taken
+// only when it is predicted to be cheaper than the last measured refactorisation.  Same matrix either way.
+static bool prefer_updown(const Engine *e, int k) {
+  if (k <= 0 || k > e->updown_max_rank) return false;
+  if (e->updown_force) return true;
+  const double t_ud = (e->npad / 32.0) * (0.030 + 0.012 * k);
+  const double t_rf = e->last_refactor_ms > 0 ? e->last_refactor_ms : 1e-9 * ((double)e->n * e->n * e->n / 3.0) / 8.0 + 0.2;
+  return t_ud < t_rf;
+}
+
 // update_sigma (iteration.c:86-145)
 static void update_sigma(QPALMWorkspace *work, Pending &pend) {
   Engine *e = eng(work);
@@ -390,7 +403,7 @@ static void update_sigma(QPALMWorkspace *work, Pending &pend) {
       (work->nb_sigma_changed > c_min(st->max_rank_update_fraction * (n + m), 0.25 * st->max_rank_update))) {
     work->solver->reset_newton = TRUE;
   } else if (work->nb_sigma_changed == 0) {
-  } else if (work->nb_sigma_changed > e->updown_max_rank) {
+  } else if (!prefer_updown(e, (int)work->nb_sigma_changed)) {
     // device cost model: beyond a few ranks a refactorisation is cheaper than sequential column sweeps
     // (same matrix either way; DESIGN.md "refactor vs update")
     work->solver->reset_newton = TRUE;
@@ -557,7 +570,7 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
       bool need_refactor = false, from_scratch = false, do_updown = false, factor_q = false;
       if ((sv->reset_newton && na) || (double)(ne + nl) > rank_limit) { need_refactor = true; from_scratch = sv->reset_newton != 0; }
       else if (na) {
-        if (ne + nl > 0) { if (ne + nl <= e->updown_max_rank) do_updown = true; else need_refactor = true; }
+        if (ne + nl > 0) { if (prefer_updown(e, ne + nl)) do_updown = true; else need_refactor = true; }
       } else factor_q = true;
       if (do_updown) {
         step_compact_lists(e);   // commits active <- candidate and lists enter / leave

@@ -38,9 +38,15 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 __global__ void __launch_bounds__(256, 1)
 k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
-           double *C, int ldc, double alpha, double beta, int lower_only) {
+           double *C, int ldc, double alpha, double beta, int lower_only,
+           long long sA, long long sB, long long sC, const int *Kz, const int *maskz) {
+  // blockIdx.z: batch instance (strides sA/sB/sC, optional per-instance K and activity mask)
   const int bm = blockIdx.x, bn = blockIdx.y;
   if (lower_only && bn > bm) return;
+  if (maskz && !maskz[blockIdx.z]) return;
+  if (Kz) K = Kz[blockIdx.z];
+  if (K <= 0 && beta == 1.0) return;
+  A += (size_t)blockIdx.z * sA; B += (size_t)blockIdx.z * sB; C += (size_t)blockIdx.z * sC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef double Tile[BK][SROW];
   Tile *As = reinterpret_cast<Tile *>(smem_raw);
@@ -137,7 +143,25 @@ int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, cons
   }
   dim3 grid(M / gemm::BM, N / gemm::BN);
   QB_LAUNCH(gemm::k_dgemm_nt, grid, 256, gemm::kSmemBytes, s, K, A, lda, B, ldb, C, ldc, alpha, beta,
-            lower_only ? 1 : 0);
+            lower_only ? 1 : 0, 0LL, 0LL, 0LL, (const int *)nullptr, (const int *)nullptr);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int dgemm_nt_batched(cudaStream_t s, int nb, int M, int N, int K, const int *Kz, const double *A, int lda, long long sA,
+                     const double *B, int ldb, long long sB, double *C, int ldc, long long sC, double alpha, double beta,
+                     bool lower_only, const int *maskz) {
+  if (M <= 0 || N <= 0 || nb <= 0) return 0;
+  if ((M % gemm::BM) || (N % gemm::BN) || (K % gemm::BK)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)gemm::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(M / gemm::BM, N / gemm::BN, nb);
+  QB_LAUNCH(gemm::k_dgemm_nt, grid, 256, gemm::kSmemBytes, s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+            lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -146,87 +170,159 @@ int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, cons
 // 128 x 128 diagonal block: Cholesky factor + inverse of the factor, one CTA, all in shared memory.
 // ================================================================================================
 namespace diag {
-constexpr int NB = 128, DS = 129, NT = 512;
-constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + NB * (NB + 1) / 2 + 3 * NB) + 16;
+// 128 x 128 diagonal block: Cholesky factor + inverse of the factor, one CTA, all in shared memory.
+// Blocked in 32-column sub-panels: a 32 x 32 block is factorised by ONE WARP in registers (row per lane,
+// pivots and multipliers exchanged with shuffles), the rows below are solved against it one row per
+// thread (row in registers, factor entries broadcast from shared memory), then all 512 threads apply the
+// rank-32 trailing update.  The inverse is formed block row by block row from the four 32 x 32 inverses.
+constexpr int NB = 128, DS = 129, NT = 512, SB = 32, RSD = 97;
+constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + NB * (NB + 1) / 2 + SB * RSD + NB) + 16;
 
 __device__ __forceinline__ int pidx(int i, int c) { return i * (i + 1) / 2 + c; }
 
-// R (packed lower, initialised to I) <- rows of inv(L) up to the final 1/dsq[i] row scaling, where
-// L(i,j) = As[i][j]/dsq[j] (i > j), L(j,j) = dsq[j], rp[j] = 1/dsq[j]^2.
-__device__ void inverse_stage(const double *As, double *Xs, const double *rp, int tid) {
-  for (int idx = tid; idx < NB * (NB + 1) / 2; idx += NT) Xs[idx] = 0.0;
-  __syncthreads();
-  for (int i = tid; i < NB; i += NT) Xs[pidx(i, i)] = 1.0;
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int j = 0; j < NB - 1; j++) {
-    __syncthreads();
-    const double r = rp[j];
-    for (int i = j + 1 + ty; i < NB; i += NT / 16) {
-      const double f = As[i * DS + j] * r;
-      for (int c = tx; c <= j; c += 16) Xs[pidx(i, c)] -= f * Xs[pidx(j, c)];
+__device__ void factor32_warp(double *As, double *rdiag, int base, int lane, int *info, int col0) {
+  double a[SB];
+#pragma unroll
+  for (int c = 0; c < SB; c++) a[c] = (c <= lane) ? As[(base + lane) * DS + base + c] : 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < SB; j++) {
+    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(pjj > 0.0) && !bad) { bad = true; if (lane == 0 && info) atomicCAS(info, 0, col0 + base + j + 1); }
+    const double ljj = sqrt(pjj), inv = 1.0 / ljj;
+    if (lane == j) { a[j] = ljj; rdiag[base + j] = inv; }
+    else if (lane > j) a[j] *= inv;
+#pragma unroll
+    for (int c = j + 1; c < SB; c++) {
+      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
     }
   }
-  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < SB; c++) if (c <= lane) As[(base + lane) * DS + base + c] = a[c];
 }
 
-// factor == 1: A block (lower) is factorised in place, then inverted.  factor == 0: the block already
+// rows i > base+31: A(i, base..base+31) <- A(i, ..) * inv(L_bb)'  by forward substitution, one row per thread
+__device__ void panel_solve(double *As, const double *rdiag, int base, int tid) {
+  const int i = base + SB + tid;
+  if (i >= NB) return;
+  double v[SB];
+#pragma unroll
+  for (int c = 0; c < SB; c++) v[c] = As[i * DS + base + c];
+#pragma unroll
+  for (int c = 0; c < SB; c++) {
+    double s = v[c];
+#pragma unroll
+    for (int t = 0; t < c; t++) s = fma(-v[t], As[(base + c) * DS + base + t], s);
+    v[c] = s * rdiag[base + c];
+  }
+#pragma unroll
+  for (int c = 0; c < SB; c++) As[i * DS + base + c] = v[c];
+}
+
+// A(i,k) -= sum_t L(i, base+t) L(k, base+t) for base+32 <= k <= i < 128
+__device__ void trailing_update(double *As, int base, int tid) {
+  const int tx = tid & 31, ty = tid >> 5, start = base + SB;
+  for (int i = start + ty; i < NB; i += NT / 32) {
+    const double *Li = As + i * DS + base;
+    for (int k = start + tx; k <= i; k += 32) {
+      const double *Lk = As + k * DS + base;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < SB; t += 2) { s0 = fma(Li[t], Lk[t], s0); s1 = fma(Li[t + 1], Lk[t + 1], s1); }
+      As[i * DS + k] -= (s0 + s1);
+    }
+  }
+}
+
+// X_bb = inv(L_bb) for the 32 x 32 diagonal block at `base`; lane = column of X
+__device__ void inv32_warp(const double *As, double *Xs, const double *rdiag, int base, int lane) {
+  double x[SB];
+#pragma unroll
+  for (int r = 0; r < SB; r++) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < r; t++) s = fma(As[(base + r) * DS + base + t], x[t], s);   // x[t] == 0 for t < lane
+    x[r] = (r < lane) ? 0.0 : ((r == lane) ? rdiag[base + r] : -s * rdiag[base + r]);
+  }
+#pragma unroll
+  for (int r = 0; r < SB; r++) if (r >= lane) Xs[pidx(base + r, base + lane)] = x[r];
+}
+
+__device__ void inverse_from_factor(const double *As, double *Xs, double *Rs, const double *rdiag, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  if (warp < 4) inv32_warp(As, Xs, rdiag, warp * SB, lane);
+  __syncthreads();
+#pragma unroll
+  for (int bi = 1; bi < 4; bi++) {
+    const int width = SB * bi, r0 = SB * bi;
+    // R = - L(block row bi, cols < r0) * X(rows < r0, cols < r0)
+    for (int idx = tid; idx < SB * width; idx += NT) {
+      const int r = idx / width, c = idx - r * width;
+      const double *Lr = As + (r0 + r) * DS;
+      double s = 0.0;
+      for (int u = c; u < r0; u++) s = fma(Lr[u], Xs[pidx(u, c)], s);
+      Rs[r * RSD + c] = -s;
+    }
+    __syncthreads();
+    // X(block row bi, cols < r0) = X_bb * R
+    for (int idx = tid; idx < SB * width; idx += NT) {
+      const int r = idx / width, c = idx - r * width;
+      double s = 0.0;
+      for (int u = 0; u <= r; u++) s = fma(Xs[pidx(r0 + r, r0 + u)], Rs[u * RSD + c], s);
+      Xs[pidx(r0 + r, c)] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// factor == 1: the block (lower) is factorised in place, then inverted.  factor == 0: the block already
 // holds a Cholesky factor (after an update/downdate sweep) and only the inverse is formed.
+// grid.x: diagonal block index (block_stride columns apart), grid.y: batch instance.
 __global__ void __launch_bounds__(NT, 1)
-k_diag_block(double *Lg, int ld, double *Xg, int *info, int col0, int factor, int block_stride) {
+k_diag_block(double *Lg, int ld, double *Xg, int *info, int col0, int factor, int block_stride,
+             long long strideL, long long strideX, const int *mask) {
+  if (mask && !mask[blockIdx.y]) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *As = reinterpret_cast<double *>(smem_raw);
   double *Xs = As + NB * DS;
-  double *rp = Xs + NB * (NB + 1) / 2;
-  double *dsq = rp + NB;
-  double *rsq = dsq + NB;
-  const int tid = threadIdx.x;
-  Lg += (size_t)blockIdx.x * block_stride * (size_t)(ld + 1);
-  Xg += (size_t)blockIdx.x * NB * NB;
+  double *Rs = Xs + NB * (NB + 1) / 2;
+  double *rdiag = Rs + SB * RSD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Lg += (size_t)blockIdx.y * strideL + (size_t)blockIdx.x * block_stride * (size_t)(ld + 1);
+  Xg += (size_t)blockIdx.y * strideX + (size_t)blockIdx.x * NB * NB;
+  if (info) info += blockIdx.y;
   col0 += blockIdx.x * block_stride;
   for (int idx = tid; idx < NB * NB; idx += NT) {
     const int i = idx & (NB - 1), k = idx >> 7;
     if (k <= i) As[i * DS + k] = Lg[i + (size_t)ld * k];
   }
-  const int tx = tid & 15, ty = tid >> 4;
+  __syncthreads();
   if (factor) {
-    for (int j = 0; j < NB; j++) {
+#pragma unroll 1
+    for (int kb = 0; kb < 4; kb++) {
+      const int base = kb * SB;
+      if (warp == 0) factor32_warp(As, rdiag, base, lane, info, col0);
       __syncthreads();
-      const double p = As[j * DS + j];
-      if (tid == 0) {
-        dsq[j] = sqrt(p); rp[j] = 1.0 / p; rsq[j] = 1.0 / sqrt(p);
-        if (!(p > 0.0)) atomicCAS(info, 0, col0 + j + 1);
-      }
-      const double r = 1.0 / p;
-      for (int i = j + 1 + ty; i < NB; i += NT / 16) {
-        const double f = As[i * DS + j] * r;
-        for (int k = j + 1 + tx; k <= i; k += 16) As[i * DS + k] -= f * As[k * DS + j];
+      if (kb < 3) {
+        panel_solve(As, rdiag, base, tid);
+        __syncthreads();
+        trailing_update(As, base, tid);
+        __syncthreads();
       }
     }
-    __syncthreads();
-    // write the factor back (lower triangle, column-major)
     for (int idx = tid; idx < NB * NB; idx += NT) {
       const int i = idx & (NB - 1), k = idx >> 7;
-      if (k < i) Lg[i + (size_t)ld * k] = As[i * DS + k] * rsq[k];
-      else if (k == i) Lg[i + (size_t)ld * k] = dsq[i];
+      if (k <= i) Lg[i + (size_t)ld * k] = As[i * DS + k];
     }
   } else {
-    __syncthreads();
-    // convert the stored factor to the "unscaled" form the inverse stage expects
-    for (int j = tid; j < NB; j += NT) {
-      const double l = As[j * DS + j];
-      dsq[j] = l; rsq[j] = 1.0 / l; rp[j] = 1.0 / (l * l);
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-      const int i = idx & (NB - 1), k = idx >> 7;
-      if (k < i) As[i * DS + k] *= dsq[k];
-    }
+    if (tid < NB) rdiag[tid] = 1.0 / As[tid * DS + tid];
     __syncthreads();
   }
-  inverse_stage(As, Xs, rp, tid);
+  inverse_from_factor(As, Xs, Rs, rdiag, tid);
   for (int idx = tid; idx < NB * NB; idx += NT) {
     const int i = idx & (NB - 1), c = idx >> 7;
-    Xg[i + (size_t)NB * c] = (c <= i) ? Xs[pidx(i, c)] * rsq[i] : 0.0;
+    Xg[i + (size_t)NB * c] = (c <= i) ? Xs[pidx(i, c)] : 0.0;
   }
 }
 }  // namespace diag
@@ -241,33 +337,55 @@ static int diag_attr() {
   return 0;
 }
 
-int potrf_lower(cudaStream_t s, int npad, double *L, int ld, double *invdiag, int *info_dev) {
+// Two-level right-looking blocked Cholesky.  Inner panels are 128 wide (diagonal block factor+inverse in one
+// CTA, panel solve as an in-place DMMA GEMM against the inverted block); their rank-128 updates are applied
+// only inside the current 512-wide outer block.  Everything to the right of the outer block receives ONE
+// rank-512 DMMA update per outer block, which amortises the C-tile read-modify-write of the trailing matrix
+// four times better than rank-128 updates.
+constexpr int kOuter = 512;
+
+int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, long long sL, double *invdiag, long long sX,
+                        int *info_dev, const int *mask) {
   if (int e = diag_attr()) return e;
-  const int nblk = npad / kPanel;
-  for (int p = 0; p < nblk; p++) {
-    const int j0 = p * kPanel;
-    double *Ljj = L + j0 + (size_t)j0 * ld;
-    double *Xp = invdiag + (size_t)p * kPanel * kPanel;
-    QB_LAUNCH(diag::k_diag_block, 1, diag::NT, diag::kSmemBytes, s, Ljj, ld, Xp, info_dev, j0, 1, 0);
-    const int rem = npad - j0 - kPanel;
-    if (rem > 0) {
+  for (int J0 = 0; J0 < npad; J0 += kOuter) {
+    const int Jend = (J0 + kOuter < npad) ? J0 + kOuter : npad;
+    for (int j0 = J0; j0 < Jend; j0 += kPanel) {
+      double *Ljj = L + j0 + (size_t)j0 * ld;
+      double *Xp = invdiag + (size_t)(j0 / kPanel) * kPanel * kPanel;
+      QB_LAUNCH(diag::k_diag_block, dim3(1, nb), diag::NT, diag::kSmemBytes, s, Ljj, ld, Xp, info_dev, j0, 1, 0, sL, sX, mask);
+      const int rem = npad - j0 - kPanel;
+      if (rem <= 0) continue;
       double *L21 = Ljj + kPanel;
       // L21 <- A21 * inv(L11)'   (in place, one 128-wide tile column)
-      if (int e = dgemm_nt(s, rem, kPanel, kPanel, L21, ld, Xp, kPanel, L21, ld, 1.0, 0.0, false)) return e;
-      // A22 <- A22 - L21 L21'    (lower tiles only)
-      double *A22 = L + (j0 + kPanel) + (size_t)(j0 + kPanel) * ld;
-      if (int e = dgemm_nt(s, rem, rem, kPanel, L21, ld, L21, ld, A22, ld, -1.0, 1.0, true)) return e;
+      if (int e = dgemm_nt_batched(s, nb, rem, kPanel, kPanel, nullptr, L21, ld, sL, Xp, kPanel, sX, L21, ld, sL, 1.0, 0.0, false, mask)) return e;
+      // rank-128 update of the remaining columns of THIS outer block (all rows below)
+      const int wcols = Jend - (j0 + kPanel);
+      if (wcols > 0) {
+        double *Cin = L + (j0 + kPanel) + (size_t)(j0 + kPanel) * ld;
+        if (int e = dgemm_nt_batched(s, nb, rem, wcols, kPanel, nullptr, L21, ld, sL, L21, ld, sL, Cin, ld, sL, -1.0, 1.0, true, mask)) return e;
+      }
+    }
+    // rank-(Jend-J0) update of everything to the right of the outer block
+    const int rem = npad - Jend;
+    if (rem > 0) {
+      const double *P = L + Jend + (size_t)J0 * ld;
+      double *A22 = L + Jend + (size_t)Jend * ld;
+      if (int e = dgemm_nt_batched(s, nb, rem, rem, Jend - J0, nullptr, P, ld, sL, P, ld, sL, A22, ld, sL, -1.0, 1.0, true, mask)) return e;
     }
   }
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
+int potrf_lower(cudaStream_t s, int npad, double *L, int ld, double *invdiag, int *info_dev) {
+  return potrf_lower_batched(s, 1, npad, L, ld, 0, invdiag, 0, info_dev, nullptr);
+}
+
 int trtri_diag_blocks(cudaStream_t s, int npad, const double *L, int ld, double *invdiag) {
   if (int e = diag_attr()) return e;
   const int nblk = npad / kPanel;
   QB_LAUNCH(diag::k_diag_block, nblk, diag::NT, diag::kSmemBytes, s, const_cast<double *>(L), ld, invdiag,
-            (int *)nullptr, 0, 0, kPanel);
+            (int *)nullptr, 0, 0, kPanel, 0LL, 0LL, (const int *)nullptr);
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -302,7 +420,9 @@ __device__ void apply_inv_lower_t(const double *__restrict__ X, const double *v_
   }
 }
 
-__global__ void __launch_bounds__(NT) k_first_fwd(const double *invdiag0, double *v) {
+__global__ void __launch_bounds__(NT) k_first_fwd(const double *invdiag0, double *v, long long sX, long long sV, const int *mask) {
+  if (mask && !mask[blockIdx.y]) return;
+  invdiag0 += (size_t)blockIdx.y * sX; v += (size_t)blockIdx.y * sV;
   __shared__ double vs[NB], scratch[2 * NB];
   if (threadIdx.x < NB) vs[threadIdx.x] = v[threadIdx.x];
   __syncthreads();
@@ -312,7 +432,9 @@ __global__ void __launch_bounds__(NT) k_first_fwd(const double *invdiag0, double
 // step b of the forward solve: rows of blocks > b get rhs -= L(rows, block b) * x_b; CTA 0 (block b+1)
 // then forms x_{b+1} = inv(L_{b+1,b+1}) rhs_{b+1}.
 __global__ void __launch_bounds__(NT) k_fwd_step(const double *__restrict__ L, int ld, const double *invdiag,
-                                                 double *v, int b) {
+                                                 double *v, int b, long long sL, long long sX, long long sV, const int *mask) {
+  if (mask && !mask[blockIdx.y]) return;
+  L += (size_t)blockIdx.y * sL; invdiag += (size_t)blockIdx.y * sX; v += (size_t)blockIdx.y * sV;
   __shared__ double xs[NB], scratch[2 * NB], rs[NB];
   const int j0 = b * NB, r0 = (b + 1 + blockIdx.x) * NB;
   const int tid = threadIdx.x, r = tid & (NB - 1), h = tid >> 7;
@@ -334,7 +456,9 @@ __global__ void __launch_bounds__(NT) k_fwd_step(const double *__restrict__ L, i
   }
 }
 
-__global__ void __launch_bounds__(NT) k_first_bwd(const double *invdiag_last, double *v_last) {
+__global__ void __launch_bounds__(NT) k_first_bwd(const double *invdiag_last, double *v_last, long long sX, long long sV, const int *mask) {
+  if (mask && !mask[blockIdx.y]) return;
+  invdiag_last += (size_t)blockIdx.y * sX; v_last += (size_t)blockIdx.y * sV;
   __shared__ double vs[NB];
   if (threadIdx.x < NB) vs[threadIdx.x] = v_last[threadIdx.x];
   __syncthreads();
@@ -344,7 +468,9 @@ __global__ void __launch_bounds__(NT) k_first_bwd(const double *invdiag_last, do
 // step b of the backward solve (b descending): columns of blocks < b get z -= L(block b rows, cols)' d_b;
 // the CTA that owns block b-1 then forms d_{b-1} = inv(L_{b-1,b-1})' z_{b-1}.
 __global__ void __launch_bounds__(NT) k_bwd_step(const double *__restrict__ L, int ld, const double *invdiag,
-                                                 double *v, int b) {
+                                                 double *v, int b, long long sL, long long sX, long long sV, const int *mask) {
+  if (mask && !mask[blockIdx.y]) return;
+  L += (size_t)blockIdx.y * sL; invdiag += (size_t)blockIdx.y * sX; v += (size_t)blockIdx.y * sV;
   __shared__ double ds[NB], zs[NB];
   const int i0 = b * NB, c0 = blockIdx.x * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -376,16 +502,21 @@ __global__ void __launch_bounds__(NT) k_bwd_step(const double *__restrict__ L, i
 }
 }  // namespace trsv
 
-int chol_solve(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v) {
+int chol_solve_batched(cudaStream_t s, int nb, int npad, const double *L, int ld, long long sL, const double *invdiag,
+                       long long sX, double *v, long long sV, const int *mask) {
   const int nblk = npad / kPanel;
-  QB_LAUNCH(trsv::k_first_fwd, 1, trsv::NT, 0, s, invdiag, v);
+  QB_LAUNCH(trsv::k_first_fwd, dim3(1, nb), trsv::NT, 0, s, invdiag, v, sX, sV, mask);
   for (int b = 0; b + 1 < nblk; b++)
-    QB_LAUNCH(trsv::k_fwd_step, nblk - 1 - b, trsv::NT, 0, s, L, ld, invdiag, v, b);
-  QB_LAUNCH(trsv::k_first_bwd, 1, trsv::NT, 0, s, invdiag + (size_t)(nblk - 1) * kPanel * kPanel,
-            v + (size_t)(nblk - 1) * kPanel);
-  for (int b = nblk - 1; b >= 1; b--) QB_LAUNCH(trsv::k_bwd_step, b, trsv::NT, 0, s, L, ld, invdiag, v, b);
+    QB_LAUNCH(trsv::k_fwd_step, dim3(nblk - 1 - b, nb), trsv::NT, 0, s, L, ld, invdiag, v, b, sL, sX, sV, mask);
+  QB_LAUNCH(trsv::k_first_bwd, dim3(1, nb), trsv::NT, 0, s, invdiag + (size_t)(nblk - 1) * kPanel * kPanel,
+            v + (size_t)(nblk - 1) * kPanel, sX, sV, mask);
+  for (int b = nblk - 1; b >= 1; b--)
+    QB_LAUNCH(trsv::k_bwd_step, dim3(b, nb), trsv::NT, 0, s, L, ld, invdiag, v, b, sL, sX, sV, mask);
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
+}
+int chol_solve(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v) {
+  return chol_solve_batched(s, 1, npad, L, ld, 0, invdiag, 0, v, 0, nullptr);
 }
 
 // ================================================================================================

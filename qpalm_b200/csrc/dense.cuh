@@ -13,6 +13,16 @@ namespace qb {
 int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, const double *B, int ldb,
              double *C, int ldc, double alpha, double beta, bool lower_only);
 
+// Batched variants (grid.z / grid.y = instance; element strides sA.. between instances; Kz: optional per-instance K,
+// maskz: optional per-instance activity flags).
+int dgemm_nt_batched(cudaStream_t s, int nb, int M, int N, int K, const int *Kz, const double *A, int lda, long long sA,
+                     const double *B, int ldb, long long sB, double *C, int ldc, long long sC, double alpha, double beta,
+                     bool lower_only, const int *maskz);
+int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, long long sL, double *invdiag, long long sX,
+                        int *info_dev, const int *mask);
+int chol_solve_batched(cudaStream_t s, int nb, int npad, const double *L, int ld, long long sL, const double *invdiag,
+                       long long sX, double *v, long long sV, const int *mask);
+
 // In-place blocked Cholesky of the lower triangle of L (npad x npad, ld).  invdiag receives the inverses
 // of the 128 x 128 diagonal blocks of the factor (npad/128 blocks, each 128 x 128 column-major, upper
 // part zero).  *info_dev (device int) is set to 1 + (first non-positive pivot column) on failure.

@@ -91,7 +91,10 @@ struct Engine {
   double alg_bytes = 0, dense_flops = 0, ms_factor = 0, ms_updown = 0, ms_total = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
   // tunables
-  int updown_max_rank = 8;
+  int updown_max_rank = 8;           // one sweep of the rank-k kernel
+  int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
+  double last_refactor_ms = -1.0;    // CUDA-event time of the most recent refactorisation (cost model input)
+  //   // device cost model: beyond this a (incremental) refactorisation is cheaper
 };
 
 // ---- construction -------------------------------------------------------------------------------

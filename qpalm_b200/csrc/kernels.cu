@@ -1491,6 +1491,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   QB_CUDA_TRY(cudaEventCreate(&e->evs0)); QB_CUDA_TRY(cudaEventCreate(&e->evs1));
   e->launches0 = g_kernel_launches;
   if (const char *s = getenv("QPALM_B200_UPDOWN_MAX_RANK")) e->updown_max_rank = atoi(s);
+  if (const char *s = getenv("QPALM_B200_UPDOWN_FORCE")) e->updown_force = atoi(s);
   QB_CUDA_TRY(cudaDeviceSynchronize());
   *out = e;
   return 0;

@@ -1,0 +1,20 @@
+"""Profiling driver for the dense Newton kernels (run under ncu): one blocked Cholesky, one SYRK, one updown sweep."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from qpalm_b200.interface import load_library
+from qpalm_b200 import abi
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
+what = sys.argv[2] if len(sys.argv) > 2 else "potrf"
+lib = load_library("b200")
+ms = C.c_double(0)
+if what == "potrf":
+    lib.qpalm_b200_bench_potrf.argtypes = [abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    rc = lib.qpalm_b200_bench_potrf(n, 1, C.byref(ms))
+    print("potrf", n, "rc", rc, "ms", ms.value, "TFLOP/s", n**3 / 3 / ms.value / 1e9)
+elif what == "syrk":
+    k = int(sys.argv[3]) if len(sys.argv) > 3 else 4000
+    lib.qpalm_b200_bench_dsyrk.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    rc = lib.qpalm_b200_bench_dsyrk(n, k, 2, C.byref(ms))
+    print("syrk", n, k, "ms", ms.value, "TFLOP/s", n * n * k / ms.value / 1e9)
