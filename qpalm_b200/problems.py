@@ -108,6 +108,55 @@ def dua_inf_qp(**settings) -> QP:
               0.0, st, expect_status=-4)
 
 
+def medium_qp(**settings) -> QP:
+    """tests/src/test_medium_qp.c:14-135 (n = m = 15, diagonal Q, 16-digit golden x)."""
+    Ap = [0, 1, 2, 5, 8, 9, 11, 12, 13, 16, 18, 21, 22, 23, 24, 25]
+    Ai = [8, 2, 1, 4, 14, 1, 4, 13, 5, 0, 7, 10, 6, 1, 4, 14, 0, 7, 1, 4, 13, 3, 9, 11, 12]
+    Ax = [0.3256021467039615, -0.2129201224283822, -0.03904780212604003, -0.01097664622926547, 8.93509853157044e-05,
+          0.1107958814061373, -0.394140028125563, -0.03422661790473164, -0.2077231940491557, 0.2961057917719591,
+          0.02901671645955232, -0.2412937540712519, 0.2180403659113273, -0.07769757105018442, -0.02184140217516474,
+          -4.490435862043659e-05, -0.007144833411941969, 0.07291061197330474, 0.01354927131911815, -0.04819953694147238,
+          0.2798798702152373, -0.316687763261202, 0.4390581348235377, -0.3143332085622074, -1.0]
+    Qx = [1.0, 0.5179474679231212, 0.2682695795279726, 0.1389495494373138, 0.07196856730011525, 0.03727593720314943,
+          0.01930697728883252, 0.01000000000000001, 0.005179474679231217, 0.002682695795279729, 0.00138949549437314,
+          0.0007196856730011531, 0.0003727593720314947, 0.0001930697728883254, 0.0001000000000000002]
+    q = [4.258643191312094, -12.7004345059705, -4.852188357430427, 5.943076168298481, -2.764649066392558,
+         -18.57582885927374, 0.4073081174942876, 2.8297017716199, 0.6356121930249937, 4.334300651115951,
+         4.228603644876851, 12.99528296551999, -10.49793234475067, -17.86411722110915, 8.16043081031918]
+    x = [-4.258643191312046e+00, 9.393193922630394e+00, 1.888905966442421e+01, -2.469934088388301e+00,
+         9.628197800226003e+00, 6.034505999261726e+00, -8.288652177085156e+00, -9.172613482098816e+00,
+         -4.005465476438092e+01, -2.983244126863757e+01, -7.447972191390734e+00, -6.315368738609618e+00,
+         4.555205430378418e+00, 6.362674847968517e+00, -2.000000000000000e+00]
+    A = _csc(15, 15, Ap, Ai, Ax)
+    Q = _csc(15, 15, list(range(16)), list(range(15)), Qx, -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, max_rank_update_fraction=1.0, verbose=0)
+    st.update(settings)
+    return QP("medium_qp", Q, A, np.array(q), -2 * np.ones(15), 2 * np.ones(15), 0.0, st,
+              expect_x=np.array(x), expect_status=1)
+
+
+def update_qp(**settings) -> QP:
+    """tests/src/test_update.c:17-97 (n=2, m=3): x* = {-0.1, 0.3}; after update_bounds {0, 0.15}; after update_q {0.02, 0.18}."""
+    A = _csc(3, 2, [0, 2, 4], [0, 2, 1, 2], [10.0, 1.0, 10.0, 1.0])
+    Q = _csc(2, 2, [0, 1, 2], [0, 1], [1.0, 1.5], -1)
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, scaling=2, proximal=1, verbose=0)
+    st.update(settings)
+    return QP("update_qp", Q, A, np.array([1.0, -2.0]), np.array([-1.0, -3.0, -0.2]), np.array([1.0, 3.0, 0.2]), 0.0, st,
+              expect_x=np.array([-0.1, 0.3]), expect_status=1)
+
+
+def solver_interface_fixture():
+    """tests/src/test_solver_interface.c:43-59,91-159: the 3 x 2 A, 2 x 2 Q (both triangles stored, stype -1) and the
+    known answers of mat_vec / mat_tpose_vec / mat_inf_norm_* / ldlchol + ldlsolveLD_neg_dphi."""
+    A = _csc(3, 2, [0, 3, 5], [0, 1, 2, 0, 1], [1.0, 3.0, 5.0, 2.0, 4.0])
+    Q = _csc(2, 2, [0, 2, 4], [0, 1, 0, 1], [1.0, -1.0, -1.0, 2.0], -1)
+    return dict(A=A, Q=Q, Qd=np.array([1.1, -0.5]), Ad=np.array([1.1, -0.5, 20.0]),
+                A_Qd=np.array([0.1, 1.3, 5.5]), Q_Qd=np.array([1.6, -2.1]), At_Ad=np.array([99.6, 0.2]),
+                col_norms=np.array([5.0, 4.0]), row_norms=np.array([2.0, 4.0, 5.0]),
+                neg_rhs=np.array([-1.0, -2.0]), d_noprox=np.array([4.0, 3.0]), gamma=1e3,
+                d_prox=np.array([3.989028924198480, 2.993017953122679]))
+
+
 # ---------------------------------------------------------------------------------------------
 # synthetic BASELINE.json configurations (SURVEY.md 8(d))
 # ---------------------------------------------------------------------------------------------
