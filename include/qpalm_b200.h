@@ -208,6 +208,11 @@ typedef struct {
   double  device_ms_total;      /* CUDA-event time of the whole qpalm_solve                            */
 } QPALMB200Stats;
 int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *out);
+/* Selective per-kernel CUDA-event timing of the library's own launches (csrc/prof.cu): `patterns` is a comma-separated
+ * list of kernel-name substrings ("*" = all, NULL/"" = off).  prof_report synchronises and writes one JSON object
+ * {"kernel": {"launches": L, "ms": T}, ...} into buf (returns the needed size when buf is NULL) and resets the log. */
+int qpalm_b200_prof_enable(const char *patterns);
+int qpalm_b200_prof_report(char *buf, size_t buflen);
 
 /* y = A x  (A m x n, CSC, stype 0)              -- replaces mat_vec,       solver_interface.c:252-262
  * y = A' x                                      -- replaces mat_tpose_vec, solver_interface.c:264-274

@@ -29,12 +29,20 @@ namespace qb {
     }                                                                                              \
   } while (0)
 
-// every kernel launch of the library goes through this counter (bench.py reports `gpu_launches`)
+// every kernel launch of the library goes through this counter (bench.py reports `gpu_launches`).
+// Selective per-kernel timing (prof.cu): when enabled for a name pattern, matching launches are bracketed by
+// CUDA events on the launching stream; bench.py reads the per-kernel launch count and device time from it
+// (the live `roofline.achieved` denominator).  Off by default: one integer test per launch.
 extern long long g_kernel_launches;
+extern int g_prof_on;
+bool prof_begin(const char *name, cudaStream_t s);
+void prof_end(cudaStream_t s);
 #define QB_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
   do {                                                                                             \
+    const bool _qb_p = qb::g_prof_on && qb::prof_begin(#kernel, (stream));                         \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                    \
     ++qb::g_kernel_launches;                                                                       \
+    if (_qb_p) qb::prof_end((stream));                                                             \
   } while (0)
 
 constexpr int kWarp = 32;

@@ -1,0 +1,89 @@
+// prof.cu -- selective per-kernel CUDA-event timing behind QB_LAUNCH (common.cuh).
+// qpalm_b200_prof_enable("k_diag_block,k_dgemm_nt") times every launch whose kernel name contains one of the
+// comma-separated patterns ("*" = all) with an event pair on the launching stream; qpalm_b200_prof_report
+// synchronises, aggregates per kernel name and writes one JSON object.  Used by bench.py for the dominant
+// kernel's average launch duration inside the timed region, and by tools/ for whole-step breakdowns.
+#include "../../include/qpalm_b200.h"
+#include "common.cuh"
+#include <map>
+#include <string>
+#include <vector>
+#include <string.h>
+
+namespace qb {
+
+int g_prof_on = 0;
+
+namespace {
+struct Rec { const char *name; cudaEvent_t e0, e1; };
+std::vector<std::string> g_patterns;
+std::vector<Rec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t g_cur0 = nullptr, g_cur1 = nullptr;
+const char *g_cur_name = nullptr;
+
+cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+bool prof_begin(const char *name, cudaStream_t s) {
+  bool hit = false;
+  for (const std::string &p : g_patterns)
+    if (p == "*" || strstr(name, p.c_str())) { hit = true; break; }
+  if (!hit) return false;
+  g_cur0 = get_event(); g_cur1 = get_event(); g_cur_name = name;
+  cudaEventRecord(g_cur0, s);
+  return true;
+}
+
+void prof_end(cudaStream_t s) {
+  cudaEventRecord(g_cur1, s);
+  g_recs.push_back({g_cur_name, g_cur0, g_cur1});
+}
+
+}  // namespace qb
+
+extern "C" int qpalm_b200_prof_enable(const char *patterns) {
+  using namespace qb;
+  g_patterns.clear();
+  if (patterns && *patterns) {
+    std::string all(patterns);
+    size_t pos = 0;
+    while (pos <= all.size()) {
+      size_t c = all.find(',', pos);
+      if (c == std::string::npos) c = all.size();
+      if (c > pos) g_patterns.push_back(all.substr(pos, c - pos));
+      pos = c + 1;
+    }
+  }
+  g_prof_on = g_patterns.empty() ? 0 : 1;
+  return 0;
+}
+
+extern "C" int qpalm_b200_prof_report(char *buf, size_t buflen) {
+  using namespace qb;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (const Rec &r : g_recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { auto &a = agg[r.name]; a.first++; a.second += ms; }
+    g_pool.push_back(r.e0); g_pool.push_back(r.e1);
+  }
+  g_recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto &kv : agg) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += tmp; first = false;
+  }
+  out += "}";
+  if (!buf || buflen == 0) return (int)out.size() + 1;
+  strncpy(buf, out.c_str(), buflen - 1);
+  buf[buflen - 1] = 0;
+  return 0;
+}

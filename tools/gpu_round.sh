@@ -1,0 +1,16 @@
+#!/bin/bash
+# One gpurun call: parity tests, smoke, bench (both arms), kernel launch lists under ncu.  Logs go to gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+nproc > gpurun_out/nproc.txt
+( time timeout 1500 python -m pytest tests -x -q -m gpu ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1
+( time timeout 1200 python bench.py --steps 3 --warmup 3 ) > gpurun_out/bench.log 2>&1
+( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/bench_ref.log 2>&1
+( time timeout 900 python bench.py --workload dense --steps 2 --warmup 3 ) > gpurun_out/bench_dense.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_batch.csv \
+   python bench.py --steps 1 --warmup 1 --no-dense --no-cpu > gpurun_out/ncu_batch.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_dense.csv \
+   python bench.py --workload dense --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_dense.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; tail -2 gpurun_out/bench.log; tail -2 gpurun_out/bench_ref.log; tail -2 gpurun_out/bench_dense.log
