@@ -10,60 +10,11 @@
 //
 // Ruiz scaling: D and E depend on A only and are shared; the cost scaling c = 1/max(1, |D q|inf) (scaling.c:84-89)
 // depends on q and is per instance, so the shared scaled Hessian is kept as D Q D and c is applied on the fly.
-#include "../../include/qpalm_b200.h"
-#include "engine.cuh"
+#include "batch.cuh"
 #include <math.h>
 #include <string.h>
-#include <vector>
 
 using namespace qb;
-
-namespace {
-
-constexpr double kInf = 1e20;
-
-struct BCtl {   // per-instance control state (device resident)
-  int iter, iter_out, prev_iter, no_change, reset_newton, gamma_maxed, done, status;
-  int nb_enter, nb_leave, nb_active, H_valid, scratch, npos, nneg, boost;
-  double gamma, gamma_prev, eps_abs_in, eps_rel_in, c, cinv, pri_res_norm, dua_res_norm, dua2_res_norm;
-  double eps_pri, eps_dua, eps_dua_in, objective, beta;
-};
-
-struct BSet {   // settings the device needs (copied by value into kernels)
-  int max_iter, inner_max_iter, proximal, scaling, reset_newton_iter, max_rank_update;
-  double eps_abs, eps_rel, eps_abs_in, eps_rel_in, rho, eps_prim_inf, eps_dual_inf, theta, delta, sigma_max, sigma_init;
-  double gamma_init, gamma_upd, gamma_max, max_rank_update_fraction, sqrt_sigma_max, data_c;
-};
-
-}  // namespace
-
-struct QPALMB200Batch {
-  int nb_max = 0, n = 0, m = 0, npad = 0, ld = 0, wcols = 0, m2 = 0;
-  cudaStream_t stream = nullptr;
-  BSet set{};
-  Engine *shared = nullptr;   // holds the shared, Ruiz-scaled At / Q (dense) and D, E
-  double *Qs = nullptr;       // n x n dense full symmetric D Q D (copy of shared->Qd before the c scaling)
-  // per-instance arrays [nb][len]
-  double *q_raw = nullptr, *bmin_raw = nullptr, *bmax_raw = nullptr, *x_out = nullptr, *y_out = nullptr;
-  double *q = nullptr, *bmin = nullptr, *bmax = nullptr, *x = nullptr, *y = nullptr, *Ax = nullptr, *Qx = nullptr, *Aty = nullptr;
-  double *x_prev = nullptr, *x0 = nullptr, *sigma = nullptr, *sigma_inv = nullptr, *sqrt_sigma = nullptr, *Axys = nullptr, *z = nullptr;
-  double *pri_res = nullptr, *pri_res_in = nullptr, *yh = nullptr, *Atyh = nullptr, *df = nullptr, *dphi = nullptr, *d = nullptr;
-  double *Qd = nullptr, *Ad = nullptr, *vpad = nullptr, *tmp_n = nullptr;
-  int *active = nullptr, *active_old = nullptr, *active_cand = nullptr, *activeH = nullptr, *list_pos = nullptr, *list_neg = nullptr;
-  double *sigmaH = nullptr, *w_pos = nullptr, *w_neg = nullptr;
-  int *Kpos = nullptr, *Kneg = nullptr;
-  double *H = nullptr, *L = nullptr, *invdiag = nullptr, *W = nullptr;
-  unsigned long long *keys = nullptr; unsigned int *vals = nullptr; double *ls_da = nullptr, *ls_db = nullptr;
-  double *scal = nullptr;
-  BCtl *ctl = nullptr;
-  int *mask_outer = nullptr, *mask_sigma = nullptr, *mask_inner = nullptr, *mask_refac = nullptr, *mask_factor = nullptr,
-      *mask_scratch = nullptr, *mask_fq = nullptr, *mask_boost = nullptr, *ndone = nullptr, *info = nullptr;
-  int *ndone_host = nullptr;
-  QPALMInfo *info_host = nullptr;
-  std::vector<BCtl> ctl_host;
-  long long launches_last = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
 
 namespace {
 
@@ -901,6 +852,10 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
   for (int **p : {&B->mask_outer, &B->mask_sigma, &B->mask_inner, &B->mask_refac, &B->mask_factor, &B->mask_scratch, &B->mask_fq, &B->mask_boost, &B->info})
     rc |= iv(p, NB);
   rc |= iv(&B->ndone, 4);
+  rc |= iv(&B->queue, 4);
+  if (const char *env = getenv("QPALM_B200_BATCH_ENGINE")) {   // tests / profiling: force one engine
+    if (!strcmp(env, "lockstep")) B->engine = 1; else if (!strcmp(env, "persistent")) B->engine = 2;
+  }
   if (rc) { fprintf(stderr, "[qpalm_b200] batch: device allocation failed\n"); qpalm_b200_batch_cleanup(B); return nullptr; }
   cudaMallocHost((void **)&B->ndone_host, sizeof(int) * 4);
   B->ctl_host.resize(NB);
@@ -930,6 +885,23 @@ extern "C" int qpalm_b200_batch_solve_resident(QPALMB200Batch *B, c_int nb_, dou
   const long long sLL = (long long)ld * npad, sX = (long long)npad * kPanel, sW = (long long)ld * B->wcols;
   const long long launches0 = g_kernel_launches;
   const int gnb = cdiv(nb, 128);
+  // engine choice: the persistent one-CTA-per-instance kernel (batchp.cu) when the shapes fit its shared-memory plan,
+  // else the lock-step engine below
+  const bool persistent = (B->engine == 2) || (B->engine == 0 && batchp_supported(n, m));
+  if (persistent) {
+    if (!batchp_supported(n, m)) { fprintf(stderr, "[qpalm_b200] batch: shapes n=%d m=%d do not fit the persistent engine\n", n, m); return 1; }
+    QB_CUDA_TRY(cudaEventRecord(B->ev0, s));
+    if (int r = batchp_solve(B, nb)) return r;
+    QB_CUDA_TRY(cudaEventRecord(B->ev1, s));
+    QB_CUDA_TRY(cudaEventSynchronize(B->ev1));
+    float msp = 0; cudaEventElapsedTime(&msp, B->ev0, B->ev1);
+    if (device_ms) *device_ms = msp;
+    B->launches_last = g_kernel_launches - launches0;
+    B->last_engine = 2;
+    QB_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  B->last_engine = 1;
   QB_CUDA_TRY(cudaEventRecord(B->ev0, s));
   QB_LAUNCH(kb_init, nb, 256, 0, s, n, m, st, e->D, e->E, B->q_raw, B->bmin_raw, B->bmax_raw, B->q, B->bmin, B->bmax, B->x, B->y, B->Ax,
             B->Qx, B->Aty, B->x_prev, B->x0, B->sigma, B->sigma_inv, B->sqrt_sigma, B->Qd, B->Ad, B->d, B->pri_res_in, B->active,
@@ -1043,7 +1015,7 @@ extern "C" void qpalm_b200_batch_cleanup(QPALMB200Batch *B) {
                   B->Qd, B->Ad, B->vpad, B->active, B->active_old, B->active_cand, B->activeH, B->list_pos, B->list_neg, B->sigmaH, B->w_pos,
                   B->w_neg, B->Kpos, B->Kneg, B->H, B->L, B->invdiag, B->W, B->keys, B->vals, B->ls_da, B->ls_db, B->scal, B->ctl,
                   B->mask_outer, B->mask_sigma, B->mask_inner, B->mask_refac, B->mask_factor, B->mask_scratch, B->mask_fq, B->mask_boost,
-                  B->ndone, B->info};
+                  B->ndone, B->info, B->queue};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (B->ndone_host) cudaFreeHost(B->ndone_host);
   if (B->ev0) cudaEventDestroy(B->ev0);

@@ -1,0 +1,1026 @@
+// batchp.cu -- persistent batch engine: ONE CTA owns one QP instance for its whole solve (BASELINE config 4).
+//
+// The lock-step engine (batch.cu) advances all instances together, one launch per step and one host poll per
+// iteration; every instance then pays for the slowest one and for ~30 launches per iteration.  Here a single kernel
+// launch solves the whole batch: CTAs pull instance indices from an atomic work queue, run the complete QPALM loop of
+// src/qpalm.c:484-711 for that instance (residuals, termination, outer updates, active set, Newton system, exact
+// line search) with block-level barriers between the steps, and take the next instance when done.  There is no host
+// synchronisation inside a solve and no instance waits for another.
+//
+// Memory plan (B200): the shared A' (n x m) and D Q D (n x n) are read by every CTA and stay in the 126 MB L2; the
+// per-instance H / L (n x n lower, column-major) and vectors are touched by one CTA only and are L2-resident while
+// the instance is in flight (3 CTAs per SM x 148 SMs in flight).  Shared memory per CTA (~70 KB, 3 CTAs / SM) holds
+// one 32-column panel of the factor (Cholesky, triangular solves, rank-32 SYRK chunks), the radix-sort buffers of the
+// line search (2m <= 2048 keys) and the staged GEMV operand.
+//
+// The Newton system (Q + A_J' Sigma_J A_J + I/gamma) d = -dphi  (src/newton.c:96-118, solver_interface.c:319-519):
+//   H is kept per instance and updated incrementally (+ entering / - leaving / +- sigma changes) by an in-CTA
+//   rank-32-chunk SYRK, L <- chol(H + beta I) by an in-CTA right-looking blocked Cholesky (32-column panels: diagonal
+//   block in one warp's registers, panel solve one row per thread, 4 x 4 register-blocked trailing update), then two
+//   blocked triangular solves.  All arithmetic is fp64 FMA (on B200 the DMMA and DFMA peaks coincide).
+#include "batch.cuh"
+#include <math.h>
+#include <string.h>
+
+using namespace qb;
+
+namespace qb {
+namespace bp {
+
+constexpr int NT = 256, NW = NT / 32;
+constexpr int PW = 32;            // panel width
+constexpr int NMAX = 240;         // largest n of this engine (panel = PW x LDP doubles of shared memory)
+constexpr int LDP = NMAX + 1;     // odd leading dimension: conflict-free row and column access
+constexpr int SORT_MAX = 2048;    // largest 2m
+constexpr int VS_LEN = 1024;      // staged GEMV operand (max(n, m) doubles)
+constexpr size_t kSortBytes = (size_t)SORT_MAX * 2 * (8 + 4) + sizeof(unsigned) * (NW * 256 + 256 + 256);
+constexpr size_t kPanelBytes = sizeof(double) * PW * LDP;
+constexpr size_t kUnionBytes = kSortBytes > kPanelBytes ? kSortBytes : kPanelBytes;
+constexpr size_t kSmemBytes = kUnionBytes + sizeof(double) * (VS_LEN + NMAX + 16 + 2 * PW);
+
+#define BSC(b, slot) P.scal[(size_t)(b) * S_COUNT + (slot)]
+
+struct Args {
+  int nb, n, m, ld;
+  BSet st;
+  const double *At, *Qs, *D, *Dinv, *E, *Einv;
+  const double *q_raw, *bmin_raw, *bmax_raw;
+  double *x_out, *y_out;
+  double *q, *bmin, *bmax, *x, *y, *Ax, *Qx, *Aty, *x_prev, *x0, *sigma, *sigma_inv, *sqrt_sigma, *Axys, *z, *pri_res, *pri_res_in,
+      *yh, *Atyh, *df, *dphi, *d, *Qd, *Ad;
+  int *active, *active_old, *active_cand, *activeH, *list_pos, *list_neg;
+  double *sigmaH, *w_pos, *w_neg;
+  double *H, *L, *rdiag;
+  long long sLL, sR;
+  unsigned long long *keys; unsigned int *vals; double *ls_da, *ls_db;
+  double *scal;
+  BCtl *ctl;
+  int *queue;
+};
+
+struct Flags { int outer, sigma, inner, refac, factor, fq, boost, done; };
+
+struct Smem {
+  unsigned char *u;      // union region: sort buffers / panel
+  double *panel;         // PW x LDP
+  double *vs;            // staged vector (VS_LEN)
+  double *v;             // Newton rhs / solution (NMAX + 16)
+  double *rd;            // 1 / l_jj of the current panel (PW), spare (PW)
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+#define RED_OUT(op, val, slot) { const double r_ = block_red<op>(val, scratch); if (threadIdx.x == 0) BSC(b, slot) = r_; }
+
+__device__ void p_init(const Args &P, int b, double *scratch) {
+  __shared__ double cc_s, sig_s;
+  const int n = P.n, m = P.m, tid = threadIdx.x;
+  const BSet &st = P.st;
+  const size_t on = (size_t)b * n, om = (size_t)b * m;
+  double mx = 0.0;
+  for (int i = tid; i < n; i += NT) {   // q <- c * (D .* q), c = 1 / max(1, |D q|inf)   (scaling.c:82-90, Qx = 0 at setup)
+    double v = P.q_raw[on + i];
+    if (st.scaling) v = P.D[i] * v;
+    P.q[on + i] = v;
+    mx = fmax(mx, fabs(v));
+  }
+  mx = block_red<RED_MAX>(mx, scratch);
+  if (tid == 0) cc_s = st.scaling ? 1 / fmax(1.0, mx) : 1.0;
+  __syncthreads();
+  const double cc = cc_s;
+  for (int i = tid; i < n; i += NT) {
+    if (st.scaling) P.q[on + i] *= cc;
+    P.x[on + i] = 0; P.Qx[on + i] = 0; P.Aty[on + i] = 0; P.x_prev[on + i] = 0; P.x0[on + i] = 0; P.Qd[on + i] = 0; P.d[on + i] = 0;
+  }
+  double dist2 = 0.0;
+  for (int i = tid; i < m; i += NT) {
+    double lo = P.bmin_raw[om + i], hi = P.bmax_raw[om + i];
+    if (st.scaling) { lo = P.E[i] * lo; hi = P.E[i] * hi; }
+    P.bmin[om + i] = lo; P.bmax[om + i] = hi;
+    P.y[om + i] = 0; P.Ax[om + i] = 0; P.Ad[om + i] = 0; P.pri_res_in[om + i] = 0;
+    P.active[om + i] = 0; P.active_old[om + i] = 0; P.activeH[om + i] = 0;
+    const double t = 0.0 - fmax(lo, fmin(0.0, hi));
+    dist2 += t * t;
+  }
+  dist2 = block_red<RED_SUM>(dist2, scratch);
+  if (tid == 0) {
+    double s = st.sigma_init * 1.0 / fmax(1.0, 0.5 * dist2);   // f = 0 at x = 0 (iteration.c:50-58)
+    s = fmax(1e-4, fmin(s, 1e4));
+    sig_s = s;
+    BCtl c;
+    memset(&c, 0, sizeof(c));
+    c.reset_newton = 1; c.gamma = st.gamma_init; c.gamma_prev = st.gamma_init; c.eps_abs_in = st.eps_abs_in; c.eps_rel_in = st.eps_rel_in;
+    c.c = cc; c.cinv = 1.0 / cc; c.status = QPALM_UNSOLVED;
+    P.ctl[b] = c;
+    for (int k = 0; k < S_COUNT; k++) BSC(b, k) = 0.0;
+  }
+  __syncthreads();
+  const double s = sig_s;
+  for (int i = tid; i < m; i += NT) { P.sigma[om + i] = s; P.sigma_inv[om + i] = 1.0 / s; P.sqrt_sigma[om + i] = sqrt(s); }
+}
+
+// compute_residuals (iteration.c:24-48) + candidate active set (newton.c:122-149) + m-side termination reductions
+__device__ void p_res_m(const Args &P, int b, double *scratch) {
+  const int m = P.m, scaling = P.st.scaling;
+  const size_t om = (size_t)b * m;
+  double r_pri = 0, r_raw = 0, r_ax = 0, r_z = 0, r_edy = 0, oob = 0, adx_max = -1.0e300, adx_min = 1.0e300;
+  double n_act = 0, n_ent = 0, n_lea = 0;
+  for (int i = threadIdx.x; i < m; i += NT) {
+    const double ax = P.Ax[om + i], yi = P.y[om + i], lo = P.bmin[om + i], hi = P.bmax[om + i];
+    double t = yi * P.sigma_inv[om + i];
+    const double axys = ax + t;
+    const double zi = fmax(lo, fmin(axys, hi));
+    const double pr = ax - zi;
+    t = pr * P.sigma[om + i];
+    const double yhi = yi + t;
+    P.Axys[om + i] = axys; P.z[om + i] = zi; P.pri_res[om + i] = pr; P.yh[om + i] = yhi;
+    const int act = (axys <= lo) || (axys >= hi);
+    const int old = P.active_old[om + i];
+    P.active_cand[om + i] = act;
+    n_act += act; n_ent += (act && !old); n_lea += (!act && old);
+    const double ei = scaling ? P.E[i] : 1.0, einv = scaling ? P.Einv[i] : 1.0;
+    r_pri = fmax(r_pri, fabs(einv * pr)); r_raw = fmax(r_raw, fabs(pr));
+    r_ax = fmax(r_ax, fabs(einv * ax)); r_z = fmax(r_z, fabs(einv * zi));
+    const double dy = yhi - yi;
+    r_edy = fmax(r_edy, fabs(ei * dy));
+    const bool hi_fin = hi < ei * kInf, lo_fin = lo > -ei * kInf;
+    oob += hi_fin ? hi * fmax(dy, 0.0) : 0.0;
+    oob += lo_fin ? lo * fmin(dy, 0.0) : 0.0;
+    const double adx = einv * P.Ad[om + i];
+    if (hi_fin) adx_max = fmax(adx_max, adx);
+    if (lo_fin) adx_min = fmin(adx_min, adx);
+  }
+  RED_OUT(RED_MAX, r_pri, S_PRI_RES) RED_OUT(RED_MAX, r_raw, S_PRI_RES_RAW) RED_OUT(RED_MAX, r_ax, S_NORM_AX)
+  RED_OUT(RED_MAX, r_z, S_NORM_Z) RED_OUT(RED_MAX, r_edy, S_NORM_EDY) RED_OUT(RED_SUM, oob, S_OOB)
+  RED_OUT(RED_MAX, adx_max, S_ADX_MAX) RED_OUT(RED_MIN, adx_min, S_ADX_MIN) RED_OUT(RED_SUM, n_act, S_NB_ACTIVE)
+  RED_OUT(RED_SUM, n_ent, S_NB_ENTER) RED_OUT(RED_SUM, n_lea, S_NB_LEAVE)
+}
+
+// out[i] = scale * sum_k M[i + ld*k] v[k], i < nrows (row sums of a shared column-major matrix: A'yh and Q d).
+// The rows are split over NT / 128-row groups: with nrows <= 128 two thread groups each take half of the columns.
+__device__ void p_gemv_rows(int nrows, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v,
+                            double *out, double scale, const Smem &S) {
+  const int tid = threadIdx.x;
+  for (int k = tid; k < ncols; k += NT) S.vs[k] = v[k];
+  __syncthreads();
+  for (int i = tid; i < nrows; i += NT) {
+    const double *r = M + i;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+    int k = 0;
+    for (; k + 7 < ncols; k += 8) {
+      a0 = fma(r[(size_t)k * ld], S.vs[k], a0);
+      a1 = fma(r[(size_t)(k + 1) * ld], S.vs[k + 1], a1);
+      a2 = fma(r[(size_t)(k + 2) * ld], S.vs[k + 2], a2);
+      a3 = fma(r[(size_t)(k + 3) * ld], S.vs[k + 3], a3);
+      a4 = fma(r[(size_t)(k + 4) * ld], S.vs[k + 4], a4);
+      a5 = fma(r[(size_t)(k + 5) * ld], S.vs[k + 5], a5);
+      a6 = fma(r[(size_t)(k + 6) * ld], S.vs[k + 6], a6);
+      a7 = fma(r[(size_t)(k + 7) * ld], S.vs[k + 7], a7);
+    }
+    for (; k < ncols; k++) a0 = fma(r[(size_t)k * ld], S.vs[k], a0);
+    out[i] = (((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))) * scale;
+  }
+}
+// out[k] = sum_i M[i + ld*k] v[i], k < ncols (column dots: A d with A' as M); one warp per column
+__device__ void p_gemv_cols(int len, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v, double *out,
+                            const Smem &S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < len; k += NT) S.vs[k] = v[k];
+  __syncthreads();
+  for (int col = warp; col < ncols; col += NW) {
+    const double *c = M + (size_t)col * ld;
+    double a0 = 0, a1 = 0;
+    int i = lane;
+    for (; i + 32 < len; i += 64) { a0 = fma(c[i], S.vs[i], a0); a1 = fma(c[i + 32], S.vs[i + 32], a1); }
+    for (; i < len; i += 32) a0 = fma(c[i], S.vs[i], a0);
+    const double acc = warp_sum(a0 + a1);
+    if (lane == 0) out[col] = acc;
+  }
+}
+
+__device__ void p_res_n(const Args &P, int b, double *scratch) {
+  const int n = P.n;
+  const BSet &st = P.st;
+  const size_t on = (size_t)b * n;
+  const double gamma = P.ctl[b].gamma, neg_inv_gamma = -1 / gamma;
+  const double neg_tau_over_gamma = -BSC(b, S_TAU) * (1 / gamma);
+  double r_dua = 0, r_dua2 = 0, r_qx = 0, r_q = 0, r_atyh = 0, r_atdy = 0, r_ddx = 0, dxdx = 0, dxqdx = 0, qdx = 0;
+  for (int j = threadIdx.x; j < n; j += NT) {
+    const double qx = P.Qx[on + j], qj = P.q[on + j], xj = P.x[on + j], at = P.Atyh[on + j];
+    double dfj = qx + qj;
+    if (st.proximal) dfj = dfj + neg_inv_gamma * P.x0[on + j];
+    const double dp = dfj + at;
+    P.df[on + j] = dfj; P.dphi[on + j] = dp;
+    const double dinv = st.scaling ? P.Dinv[j] : 1.0;
+    if (st.proximal) {
+      const double xx0 = xj - P.x0[on + j];
+      const double t = dp + neg_inv_gamma * xx0;
+      r_dua = fmax(r_dua, fabs(dinv * t));
+    } else r_dua = fmax(r_dua, fabs(dinv * dp));
+    r_dua2 = fmax(r_dua2, fabs(dinv * dp));
+    r_qx = fmax(r_qx, fabs(dinv * qx)); r_q = fmax(r_q, fabs(dinv * qj)); r_atyh = fmax(r_atyh, fabs(dinv * at));
+    r_atdy = fmax(r_atdy, fabs(dinv * (at - P.Aty[on + j])));
+    const double dx = xj - P.x_prev[on + j];
+    const double ddx = st.scaling ? P.D[j] * dx : dx;
+    r_ddx = fmax(r_ddx, fabs(ddx));
+    dxdx += ddx * ddx;
+    if (st.proximal) { const double t2 = P.Qd[on + j] + neg_tau_over_gamma * P.d[on + j]; dxqdx += dx * t2; }
+    else dxqdx += P.Qd[on + j] * dx;
+    qdx += qj * dx;
+  }
+  RED_OUT(RED_MAX, r_dua, S_DUA_RES) RED_OUT(RED_MAX, r_dua2, S_DUA2_RES) RED_OUT(RED_MAX, r_qx, S_NORM_QX)
+  RED_OUT(RED_MAX, r_q, S_NORM_Q) RED_OUT(RED_MAX, r_atyh, S_NORM_ATYH) RED_OUT(RED_MAX, r_atdy, S_NORM_ATDY)
+  RED_OUT(RED_MAX, r_ddx, S_NORM_DDX) RED_OUT(RED_SUM, dxdx, S_DXDX) RED_OUT(RED_SUM, dxqdx, S_DXQDX) RED_OUT(RED_SUM, qdx, S_QDX)
+}
+
+// the control flow of qpalm_solve for one iteration (src/qpalm.c:484-711), executed by one thread
+__device__ void p_control(const Args &P, int b, Flags &f) {
+  const BSet &st = P.st;
+  const int n = P.n, m = P.m;
+  f.outer = f.sigma = f.inner = f.refac = f.factor = f.fq = f.boost = f.done = 0;
+  BCtl c = P.ctl[b];
+  const double *h = P.scal + (size_t)b * S_COUNT;
+  const double cinv = st.scaling ? c.cinv : 1.0;
+  c.pri_res_norm = h[S_PRI_RES];
+  c.dua_res_norm = h[S_DUA_RES] * cinv;
+  c.dua2_res_norm = h[S_DUA2_RES] * cinv;
+  const double nrm_axz = st.scaling ? h[S_NORM_AX] : fmax(h[S_NORM_AX], h[S_NORM_Z]);   // sic, termination.c:99
+  c.eps_pri = st.eps_abs + st.eps_rel * nrm_axz;
+  double max_norm = fmax(h[S_NORM_QX], fmax(h[S_NORM_Q], h[S_NORM_ATYH]));
+  if (st.scaling) max_norm *= cinv;
+  c.eps_dua = st.eps_abs + st.eps_rel * max_norm;
+  c.eps_dua_in = c.eps_abs_in + c.eps_rel_in * max_norm;
+  int term = 0;
+  if ((c.pri_res_norm < c.eps_pri) && (c.dua_res_norm < c.eps_dua)) term = QPALM_SOLVED;
+  else {
+    const double eps_pinf = st.eps_prim_inf * h[S_NORM_EDY];
+    if ((eps_pinf != 0) && (h[S_NORM_ATDY] <= eps_pinf) && (h[S_OOB] <= -eps_pinf)) term = QPALM_PRIMAL_INFEASIBLE;
+    else {
+      const double eps_dinf = st.eps_dual_inf * h[S_NORM_DDX];
+      if (eps_dinf != 0) {
+        const bool blocked = (m > 0) && ((h[S_ADX_MAX] >= eps_dinf) || (h[S_ADX_MIN] <= -eps_dinf));
+        if (!blocked) {
+          const double cc = st.scaling ? c.c : 1.0, e2 = st.eps_dual_inf * st.eps_dual_inf;
+          if ((h[S_DXQDX] <= -cc * e2 * h[S_DXDX]) || ((h[S_DXQDX] <= cc * e2 * h[S_DXDX]) && (h[S_QDX] <= -cc * eps_dinf)))
+            term = QPALM_DUAL_INFEASIBLE;
+        }
+      }
+    }
+  }
+  if (term) { c.status = term; c.done = 1; P.ctl[b] = c; f.done = 1; return; }
+  const int na = (m > 0) ? (int)h[S_NB_ACTIVE] : 0, ne = (m > 0) ? (int)h[S_NB_ENTER] : 0, nl = (m > 0) ? (int)h[S_NB_LEAVE] : 0;
+  if ((c.dua2_res_norm <= c.eps_dua_in) || (c.no_change == 3)) {   // qpalm.c:515
+    c.no_change = 0;
+    f.outer = 1;
+    if (c.iter_out > 0 && c.pri_res_norm > c.eps_pri) f.sigma = 1;
+    c.eps_abs_in = fmax(st.eps_abs, st.rho * c.eps_abs_in);
+    c.eps_rel_in = fmax(st.eps_rel, st.rho * c.eps_rel_in);
+    c.gamma_prev = c.gamma;
+    if (st.proximal) {
+      const bool try_boost = !c.gamma_maxed && c.iter_out > 0 && c.nb_enter == 0 && c.nb_leave == 0 && c.pri_res_norm < c.eps_pri;
+      if (try_boost) f.boost = 1;
+      else if (c.gamma < st.gamma_max) { c.gamma = fmin(c.gamma * st.gamma_upd, st.gamma_max); c.reset_newton = 1; }
+    }
+    c.iter_out++; c.prev_iter = c.iter;
+  } else if (c.iter == c.prev_iter + st.inner_max_iter) {   // qpalm.c:647-660
+    c.no_change = 0;
+    f.outer = 2;
+    if (c.iter_out > 0 && c.pri_res_norm > c.eps_pri) f.sigma = 1;
+    c.gamma_prev = c.gamma;
+    if (st.proximal && c.gamma < st.gamma_max) { c.gamma = fmin(c.gamma * st.gamma_upd, st.gamma_max); c.reset_newton = 1; }
+    c.iter_out++; c.prev_iter = c.iter;
+  } else {   // inner step
+    if (c.nb_enter + c.nb_leave) c.no_change = 0; else c.no_change++;
+    if ((c.iter % st.reset_newton_iter) == 0) c.reset_newton = 1;
+    c.nb_active = na; c.nb_enter = ne; c.nb_leave = nl;
+    f.inner = 1;
+    c.beta = st.proximal ? 1.0 / c.gamma : 0.0;
+    const double rank_limit = fmin(st.max_rank_update_fraction * (double)(n + m), (double)st.max_rank_update);
+    c.scratch = 0;
+    if ((c.reset_newton && na) || (double)(ne + nl) > rank_limit) { f.refac = 1; f.factor = 1; c.scratch = c.reset_newton || !c.H_valid; }
+    else if (na) { if (ne + nl > 0) { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
+    else { f.fq = 1; f.factor = 1; }
+    c.reset_newton = 0;
+  }
+  P.ctl[b] = c;
+}
+
+// update_sigma (iteration.c:86-145); every sigma change leads to a refactorisation (same matrix as the reference's
+// rank update of solver_interface.c:443-503)
+__device__ void p_update_sigma(const Args &P, int b, double *scratch) {
+  const int m = P.m;
+  const BSet &st = P.st;
+  const size_t om = (size_t)b * m;
+  const double nrm = BSC(b, S_PRI_RES_RAW);
+  double changed = 0;
+  for (int k = threadIdx.x; k < m; k += NT) {
+    const double pr = fabs(P.pri_res[om + k]);
+    if ((pr > st.theta * fabs(P.pri_res_in[om + k])) && P.active[om + k]) {
+      double mult = fmax(1.0, st.delta * pr / (nrm + 1e-6));
+      const double sg = P.sigma[om + k], stmp = mult * sg;
+      if (stmp <= st.sigma_max) {
+        changed += (sg != stmp);
+        P.sigma[om + k] = stmp; P.sigma_inv[om + k] = 1.0 / stmp;
+        mult = sqrt(mult);
+        P.sqrt_sigma[om + k] = mult * P.sqrt_sigma[om + k];
+      } else {
+        changed += (sg != st.sigma_max);
+        P.sigma[om + k] = st.sigma_max; P.sigma_inv[om + k] = 1.0 / st.sigma_max; P.sqrt_sigma[om + k] = st.sqrt_sigma_max;
+      }
+    }
+  }
+  changed = block_red<RED_SUM>(changed, scratch);
+  if (threadIdx.x == 0) {
+    if ((st.proximal && P.ctl[b].gamma_prev < st.gamma_max) || changed > 0) P.ctl[b].reset_newton = 1;
+  }
+}
+
+// y <- yh, Aty <- Atyh, Qx += (1/gamma - 1/gamma_prev) x, x0 <- x, pri_res_in <- pri_res (qpalm.c:525-526, 629, 635, 655, 658)
+__device__ void p_outer(const Args &P, int b, int kind) {
+  const int n = P.n, m = P.m;
+  const size_t on = (size_t)b * n, om = (size_t)b * m;
+  const double g = P.ctl[b].gamma, gp = P.ctl[b].gamma_prev;
+  const double dg = (g != gp) ? (1 / g - 1 / gp) : 0.0;
+  for (int i = threadIdx.x; i < m; i += NT) {
+    if (kind == 1) P.y[om + i] = P.yh[om + i];
+    P.pri_res_in[om + i] = P.pri_res[om + i];
+  }
+  for (int j = threadIdx.x; j < n; j += NT) {
+    if (kind == 1) P.Aty[on + j] = P.Atyh[on + j];
+    if (P.st.proximal) {
+      if (dg != 0.0) P.Qx[on + j] = P.Qx[on + j] + dg * P.x[on + j];
+      P.x0[on + j] = P.x[on + j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense building blocks on an n x n lower matrix in global memory (L2 resident), panels in shared memory
+// ------------------------------------------------------------------------------------------------
+// dst(i, j) = [first ? sscale * src(i, j) + (i == j) * diag_add : dst(i, j)] + sign * sum_{c < w} U[c][i - u0] U[c][j - u0]
+// for r0 <= j <= i < n.  U is PW x LDP in shared memory.  Warp task = 128 rows x 4 columns, 4 x 4 register block per lane.
+__device__ void cta_rank_update_lower(double *dst, int ldd, const double *src, int lds, double sscale, double diag_add, bool first,
+                                      int r0, int n, const double *U, int u0, int w, double sign) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rem = n - r0;
+  if (rem <= 0) return;
+  const int IB = (rem + 127) / 128, JB = (rem + 3) / 4;
+  for (int q = warp; q < IB * JB; q += NW) {
+    const int ib = q / JB, jb = q - ib * JB;
+    const int i0 = r0 + ib * 128, j0 = r0 + jb * 4;
+    if (i0 + 127 < j0) continue;   // block entirely above the diagonal
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[a][e] = 0.0;
+    int ri[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { ri[a] = i0 + lane + 32 * a; if (ri[a] >= n) ri[a] = n - 1; }
+    int cj[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) { cj[e] = j0 + e; if (cj[e] >= n) cj[e] = n - 1; }
+    for (int c = 0; c < w; c++) {
+      const double *Uc = U + c * LDP - u0;
+      double ua[4], ub[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) ua[a] = Uc[ri[a]];
+#pragma unroll
+      for (int e = 0; e < 4; e++) ub[e] = Uc[cj[e]];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[a][e] = fma(ua[a], ub[e], acc[a][e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int j = j0 + e;
+      if (j >= n) continue;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int i = i0 + lane + 32 * a;
+        if (i >= n || i < j) continue;
+        double base;
+        if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
+        else base = dst[(size_t)i + (size_t)ldd * j];
+        dst[(size_t)i + (size_t)ldd * j] = base + sign * acc[a][e];
+      }
+    }
+  }
+}
+
+// Cholesky of the w x w diagonal block held in the panel (rows/cols 0..w-1 of P[t][r]); warp 0 only.  Rows >= w act
+// as identity rows so that the 32-wide register code needs no special cases.  rd[j] = 1 / l_jj.
+__device__ void warp_factor_diag(double *Pn, double *rd, int w, int *info) {
+  const int lane = threadIdx.x & 31;
+  double a[PW];
+#pragma unroll
+  for (int c = 0; c < PW; c++) a[c] = (lane < w && c < w) ? ((c <= lane) ? Pn[c * LDP + lane] : 0.0) : ((c == lane) ? 1.0 : 0.0);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < PW; j++) {
+    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(pjj > 0.0)) bad = true;
+    const double ljj = sqrt(pjj), inv = 1.0 / ljj;
+    if (lane == j) { a[j] = ljj; rd[j] = inv; }
+    else if (lane > j) a[j] *= inv;
+#pragma unroll
+    for (int c = j + 1; c < PW; c++) {
+      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < PW; c++) if (c <= lane && lane < w) Pn[c * LDP + lane] = a[c];
+  if (bad && lane == 0 && info) *info = 1;
+}
+
+// L <- chol(sscale * src + beta I) (lower, n x n), right-looking with PW-column panels.  rdiag_g[j] = 1 / l_jj.
+__device__ void cta_potrf(double *L, int ld, const double *src, int lds, double sscale, double beta, int n, double *rdiag_g,
+                          const Smem &S, int *info) {
+  const int tid = threadIdx.x;
+  double *Pn = S.panel;
+  for (int k0 = 0; k0 < n; k0 += PW) {
+    const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
+    const bool first = (k0 == 0);
+    for (int idx = tid; idx < w * rows; idx += NT) {   // panel load, rows fastest (coalesced)
+      const int t = idx / rows, r = idx - t * rows;
+      const int i = k0 + r, j = k0 + t;
+      double v = 0.0;
+      if (r >= t) {
+        if (first) { v = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) v += beta; }
+        else v = L[(size_t)i + (size_t)ld * j];
+      }
+      Pn[t * LDP + r] = v;
+    }
+    __syncthreads();
+    if (tid < 32) warp_factor_diag(Pn, S.rd, w, info);
+    __syncthreads();
+    for (int r = w + tid; r < rows; r += NT) {   // rows below the diagonal block: forward substitution, one row per thread
+      double v[PW];
+#pragma unroll
+      for (int c = 0; c < PW; c++) v[c] = (c < w) ? Pn[c * LDP + r] : 0.0;
+#pragma unroll
+      for (int c = 0; c < PW; c++) {
+        if (c < w) {
+          double s = v[c];
+#pragma unroll
+          for (int t = 0; t < c; t++) s = fma(-v[t], Pn[t * LDP + c], s);
+          v[c] = s * S.rd[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PW; c++) if (c < w) Pn[c * LDP + r] = v[c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * rows; idx += NT) {   // final columns of L
+      const int t = idx / rows, r = idx - t * rows;
+      if (r >= t) L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] = Pn[t * LDP + r];
+    }
+    if (tid < w) rdiag_g[k0 + tid] = S.rd[tid];
+    cta_rank_update_lower(L, ld, src, lds, sscale, beta, first, k0 + w, n, Pn, k0, w, -1.0);
+    __syncthreads();
+  }
+}
+
+// v <- (L L')^{-1} v, v in shared memory (S.v), L n x n lower in global memory, rdiag_g = 1 / diag(L)
+__device__ void cta_chol_solve(const double *L, int ld, int n, const double *rdiag_g, const Smem &S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *Pn = S.panel, *v = S.v;
+  // forward: L z = v
+  for (int k0 = 0; k0 < n; k0 += PW) {
+    const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
+    for (int idx = tid; idx < w * rows; idx += NT) {
+      const int t = idx / rows, r = idx - t * rows;
+      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double vl = (lane < w) ? v[k0 + lane] : 0.0;
+      const double rd = (lane < w) ? rdiag_g[k0 + lane] : 1.0;
+      for (int j = 0; j < w; j++) {
+        const double zj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
+        if (lane == j) vl = zj;
+        else if (lane > j && lane < w) vl = fma(-Pn[j * LDP + lane], zj, vl);
+      }
+      if (lane < w) v[k0 + lane] = vl;
+    }
+    __syncthreads();
+    for (int r = w + tid; r < rows; r += NT) {
+      double s0 = 0.0, s1 = 0.0;
+      int t = 0;
+      for (; t + 1 < w; t += 2) { s0 = fma(Pn[t * LDP + r], v[k0 + t], s0); s1 = fma(Pn[(t + 1) * LDP + r], v[k0 + t + 1], s1); }
+      if (t < w) s0 = fma(Pn[t * LDP + r], v[k0 + t], s0);
+      v[k0 + r] -= (s0 + s1);
+    }
+    __syncthreads();
+  }
+  // backward: L' d = z
+  const int last = ((n - 1) / PW) * PW;
+  for (int k0 = last; k0 >= 0; k0 -= PW) {
+    const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
+    for (int idx = tid; idx < w * rows; idx += NT) {
+      const int t = idx / rows, r = idx - t * rows;
+      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
+    }
+    __syncthreads();
+    for (int t = warp; t < w; t += NW) {   // v[k0 + t] -= sum_{r >= w} L(k0 + r, k0 + t) d(k0 + r)
+      double s = 0.0;
+      for (int r = w + lane; r < rows; r += 32) s = fma(Pn[t * LDP + r], v[k0 + r], s);
+      s = warp_sum(s);
+      if (lane == 0) S.rd[PW + t] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double vl = (lane < w) ? v[k0 + lane] - S.rd[PW + lane] : 0.0;
+      const double rd = (lane < w) ? rdiag_g[k0 + lane] : 1.0;
+      for (int j = w - 1; j >= 0; j--) {
+        const double dj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
+        if (lane == j) vl = dj;
+        else if (lane < j) vl = fma(-Pn[lane * LDP + j], dj, vl);   // L(k0 + j, k0 + lane)
+      }
+      if (lane < w) v[k0 + lane] = vl;
+    }
+    __syncthreads();
+  }
+}
+
+// dst(lower) += sign * sum_{c < cnt} (wgt[c] A'[:, list[c]]) (...)'   in chunks of PW list entries staged in the panel
+__device__ void cta_syrk_list(double *dst, int ld, int n, const double *__restrict__ At, const int *__restrict__ list,
+                              const double *__restrict__ wgt, int cnt, double sign, const Smem &S) {
+  const int tid = threadIdx.x;
+  for (int off = 0; off < cnt; off += PW) {
+    const int w = (cnt - off < PW) ? cnt - off : PW;
+    for (int idx = tid; idx < w * n; idx += NT) {
+      const int c = idx / n, i = idx - c * n;
+      S.panel[c * LDP + i] = wgt[off + c] * At[(size_t)i + (size_t)n * list[off + c]];
+    }
+    __syncthreads();
+    cta_rank_update_lower(dst, ld, nullptr, 0, 0.0, 0.0, false, 0, n, S.panel, 0, w, sign);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// active-set commit + ordered H-difference lists (batch.cu kb_lists, one CTA)
+// ------------------------------------------------------------------------------------------------
+__device__ void p_lists(const Args &P, int b, int refac) {
+  __shared__ int warp_cnt0[NW], warp_cnt1[NW];
+  __shared__ int base0, base1, redo;
+  const int m = P.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t om = (size_t)b * m;
+  for (int i = tid; i < m; i += NT) P.active[om + i] = P.active_cand[om + i];
+  if (!refac) return;
+  int scratch_mode = P.ctl[b].scratch;
+  const int nb_active = P.ctl[b].nb_active;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    __syncthreads();
+    if (tid == 0) { base0 = 0; base1 = 0; redo = 0; }
+    __syncthreads();
+    for (int start = 0; start < m; start += NT) {
+      const int i = start + tid;
+      bool p0 = false, p1 = false;
+      double s0 = 0.0, s1 = 0.0;
+      if (i < m) {
+        const int a = P.active[om + i];
+        const double wn = a ? P.sigma[om + i] : 0.0;
+        const double wh = (scratch_mode || !P.activeH[om + i]) ? 0.0 : P.sigmaH[om + i];
+        const double dw = wn - wh;
+        if (dw > 0.0) { p0 = true; s0 = (wh == 0.0) ? P.sqrt_sigma[om + i] : sqrt(dw); }
+        else if (dw < 0.0) { p1 = true; s1 = sqrt(-dw); }
+      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+      if (lane == 0) { warp_cnt0[warp] = __popc(b0); warp_cnt1[warp] = __popc(b1); }
+      __syncthreads();
+      int off0 = base0, off1 = base1;
+      for (int w = 0; w < warp; w++) { off0 += warp_cnt0[w]; off1 += warp_cnt1[w]; }
+      const unsigned lt = (1u << lane) - 1u;
+      if (p0) { const int pos = off0 + __popc(b0 & lt); P.list_pos[om + pos] = i; P.w_pos[om + pos] = s0; }
+      if (p1) { const int pos = off1 + __popc(b1 & lt); P.list_neg[om + pos] = i; P.w_neg[om + pos] = s1; }
+      __syncthreads();
+      if (tid == 0) { int t0 = 0, t1 = 0; for (int w = 0; w < NW; w++) { t0 += warp_cnt0[w]; t1 += warp_cnt1[w]; } base0 += t0; base1 += t1; }
+      __syncthreads();
+    }
+    if (tid == 0 && !scratch_mode && base0 + base1 > nb_active) redo = 1;   // cheaper to rebuild from Q
+    __syncthreads();
+    if (!redo) break;
+    scratch_mode = 1;
+  }
+  for (int i = tid; i < m; i += NT) { P.activeH[om + i] = P.active[om + i]; P.sigmaH[om + i] = P.sigma[om + i]; }
+  if (tid == 0) {
+    BCtl &c = P.ctl[b];
+    c.npos = base0; c.nneg = base1; c.H_valid = 1; c.scratch = scratch_mode;
+  }
+}
+
+// ordered list of the active rows with weights sqrt(sigma) (boost_gamma's A_J' Sigma_J A_J)
+__device__ void p_active_list(const Args &P, int b) {
+  __shared__ int warp_cnt[NW];
+  __shared__ int base;
+  const int m = P.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t om = (size_t)b * m;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int start = 0; start < m; start += NT) {
+    const int i = start + tid;
+    const bool p = (i < m) && P.active[om + i];
+    const unsigned bl = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) warp_cnt[warp] = __popc(bl);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; w++) off += warp_cnt[w];
+    if (p) { const int pos = off + __popc(bl & ((1u << lane) - 1u)); P.list_pos[om + pos] = i; P.w_pos[om + pos] = P.sqrt_sigma[om + i]; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < NW; w++) t += warp_cnt[w]; base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) P.ctl[b].npos = base;
+}
+
+// boost_gamma path of the outer update (qpalm.c:613-627, iteration.c:159-211).  Returns with gamma / reset_newton set.
+__device__ void p_boost(const Args &P, int b, double *scratch, const Smem &S) {
+  __shared__ int need_gersh;
+  const int n = P.n, m = P.m, tid = threadIdx.x;
+  const BSet &st = P.st;
+  const size_t om = (size_t)b * m, on = (size_t)b * n;
+  double na = 0, ne = 0, nl = 0;
+  for (int i = tid; i < m; i += NT) {
+    const double t = P.y[om + i] / P.sigma[om + i];
+    const double a = P.Ax[om + i] + t;
+    P.Axys[om + i] = a;
+    const int act = (a <= P.bmin[om + i]) || (a >= P.bmax[om + i]);
+    P.active[om + i] = act;
+    na += act; ne += act && !P.active_old[om + i]; nl += !act && P.active_old[om + i];
+  }
+  na = block_red<RED_SUM>(na, scratch); ne = block_red<RED_SUM>(ne, scratch); nl = block_red<RED_SUM>(nl, scratch);
+  if (tid == 0) {
+    BCtl &c = P.ctl[b];
+    c.nb_active = (int)na; c.nb_enter = (int)ne; c.nb_leave = (int)nl; c.boost = 0;
+    need_gersh = 0;
+    if (ne == 0 && nl == 0) {
+      c.boost = 1;
+      if (na == 0) { c.gamma = 1e12; c.reset_newton = 1; }   // iteration.c:198-200
+      else { c.scratch = 1; c.npos = 0; c.nneg = 0; need_gersh = 1; }
+    } else if (c.gamma < st.gamma_max) { c.gamma = fmin(c.gamma * st.gamma_upd, st.gamma_max); c.reset_newton = 1; }
+  }
+  __syncthreads();
+  if (need_gersh) {
+    p_active_list(P, b);
+    __syncthreads();
+    double *Lb = P.L + (size_t)b * P.sLL;
+    const int ld = P.ld;
+    for (int idx = tid; idx < n * n; idx += NT) { const int j = idx / n, i = idx - j * n; if (i >= j) Lb[(size_t)i + (size_t)ld * j] = 0.0; }
+    __syncthreads();
+    cta_syrk_list(Lb, ld, n, P.At, P.list_pos + om, P.w_pos + om, P.ctl[b].npos, 1.0, S);
+    __syncthreads();
+    double ub = -1.0e300;
+    for (int i = tid; i < n; i += NT) {   // Gershgorin: |row i| of the symmetric matrix
+      double acc = 0.0;
+      for (int j = 0; j <= i; j++) acc += fabs(Lb[(size_t)i + (size_t)j * ld]);
+      for (int j = i + 1; j < n; j++) acc += fabs(Lb[(size_t)j + (size_t)i * ld]);
+      ub = fmax(ub, acc);
+    }
+    ub = block_red<RED_MAX>(ub, scratch);
+    if (tid == 0) {
+      BCtl &c = P.ctl[b];
+      c.gamma = fmax(st.gamma_max, 1e14 / ub);
+      c.gamma_maxed = 1;
+      c.reset_newton = 1;
+    }
+    __syncthreads();
+  }
+  // Qx / Qd shifts for a changed gamma (iteration.c:205-209); the Qd shift belongs to boost_gamma only
+  const double g = P.ctl[b].gamma, gp = P.ctl[b].gamma_prev;
+  if (g != gp) {
+    const double tau = BSC(b, S_TAU);
+    const int boosted = P.ctl[b].boost;
+    for (int j = tid; j < n; j += NT) {
+      P.Qx[on + j] = P.Qx[on + j] + (1.0 / g - 1.0 / gp) * P.x[on + j];
+      if (boosted) P.Qd[on + j] = P.Qd[on + j] + (tau / g - tau / gp) * P.d[on + j];
+    }
+    __syncthreads();
+    if (tid == 0) P.ctl[b].reset_newton = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// line search (linesearch.c:14-120)
+// ------------------------------------------------------------------------------------------------
+__device__ void p_ls_build(const Args &P, int b, double *scratch) {
+  const int n = P.n, m = P.m;
+  const size_t on = (size_t)b * n, om = (size_t)b * m, o2 = (size_t)b * 2 * m;
+  const double inv_gamma = 1 / P.ctl[b].gamma;
+  double eta = 0, beta = 0;
+  for (int j = threadIdx.x; j < n; j += NT) {
+    double qd = P.Qd[on + j];
+    const double dj = P.d[on + j];
+    if (P.st.proximal) { qd = qd + inv_gamma * dj; P.Qd[on + j] = qd; }
+    eta += dj * qd; beta += dj * P.df[on + j];
+  }
+  double a_part = 0, b_part = 0, n_l = 0;
+  for (int i = threadIdx.x; i < m; i += NT) {
+    const double ss = P.sqrt_sigma[om + i], sg = P.sigma[om + i], ax = P.Ax[om + i], yi = P.y[om + i];
+    const double t = ss * P.Ad[om + i];
+    double dl[2], al[2];
+    dl[1] = t; dl[0] = t * -1;
+    double u = ax - P.bmin[om + i]; u = sg * u; u = yi + u; al[0] = u / ss;
+    u = P.bmax[om + i] - ax; u = sg * u; u = u - yi; al[1] = u / ss;
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int idx = i + hh * m;
+      const double s = al[hh] / dl[hh];
+      const bool inL = s > 0, inP = dl[hh] > 0;
+      P.keys[o2 + idx] = inL ? (unsigned long long)__double_as_longlong(s) : ~0ull;
+      P.vals[o2 + idx] = (unsigned int)idx;
+      const double d2 = dl[hh] * dl[hh], dalp = dl[hh] * al[hh];
+      P.ls_da[o2 + idx] = inP ? d2 : -d2;
+      P.ls_db[o2 + idx] = inP ? -dalp : dalp;
+      if ((int)inL + (int)inP == 1) { a_part += d2; b_part += dalp; }
+      n_l += inL;
+    }
+  }
+  RED_OUT(RED_SUM, eta, S_ETA) RED_OUT(RED_SUM, beta, S_BETA) RED_OUT(RED_SUM, a_part, S_LS_A)
+  RED_OUT(RED_SUM, b_part, S_LS_B) RED_OUT(RED_SUM, n_l, S_NL)
+}
+
+// stable LSD radix sort of N <= SORT_MAX (key, val) pairs in shared memory; sorted pairs are written back to global
+__device__ void p_sort(int N, unsigned long long *kg, unsigned int *vg, const Smem &S) {
+  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(S.u), *k1 = k0 + SORT_MAX;
+  unsigned int *v0 = reinterpret_cast<unsigned int *>(k1 + SORT_MAX), *v1 = v0 + SORT_MAX;
+  unsigned int *warp_cnt = v1 + SORT_MAX;            // [NW][256]
+  unsigned int *running = warp_cnt + NW * 256;       // [256]
+  unsigned int *hist = running + 256;                // [256]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < N; i += NT) { k0[i] = kg[i]; v0[i] = vg[i]; }
+  __syncthreads();
+  unsigned long long *kin = k0, *kout = k1;
+  unsigned int *vin = v0, *vout = v1;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = pass * 8;
+    hist[tid] = 0;   // NT == 256
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) atomicAdd(&hist[(unsigned)(kin[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (hist[(unsigned)(kin[0] >> shift) & 255u] == (unsigned)N) { __syncthreads(); continue; }   // all keys share this digit
+    if (warp == 0) {
+      unsigned int loc[8], sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) { loc[t] = hist[lane * 8 + t]; sum += loc[t]; }
+      unsigned int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+      unsigned int run = inc - sum;
+#pragma unroll
+      for (int t = 0; t < 8; t++) { running[lane * 8 + t] = run; run += loc[t]; }
+    }
+    __syncthreads();
+    for (int start = 0; start < N; start += NT) {
+      for (int i = tid; i < NW * 256; i += NT) warp_cnt[i] = 0;
+      __syncthreads();
+      const int e = start + tid;
+      const bool valid = e < N;
+      unsigned long long k = 0; unsigned int v = 0; unsigned int dg = 0x10000u + lane;
+      if (valid) { k = kin[e]; v = vin[e]; dg = (unsigned)(k >> shift) & 255u; }
+      const unsigned peers = __match_any_sync(0xffffffffu, dg);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      if (valid && rank == 0) warp_cnt[warp * 256 + dg] = __popc(peers);
+      __syncthreads();
+      if (valid) {
+        unsigned int off = running[dg];
+        for (int w = 0; w < warp; w++) off += warp_cnt[w * 256 + dg];
+        kout[off + rank] = k; vout[off + rank] = v;
+      }
+      __syncthreads();
+      {
+        unsigned int t = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) t += warp_cnt[w * 256 + tid];
+        running[tid] += t;
+      }
+      __syncthreads();
+    }
+    unsigned long long *tk = kin; kin = kout; kout = tk;
+    unsigned int *tv = vin; vin = vout; vout = tv;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += NT) { kg[i] = kin[i]; vg[i] = vin[i]; }
+}
+
+__device__ void p_ls_select(const Args &P, int b) {
+  __shared__ double wa[NW], wb[NW];
+  __shared__ double carry_a, carry_b;
+  __shared__ int found;
+  const size_t o2 = (size_t)b * 2 * P.m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nL = (int)BSC(b, S_NL);
+  if (tid == 0) { carry_a = BSC(b, S_ETA) + BSC(b, S_LS_A); carry_b = BSC(b, S_BETA) - BSC(b, S_LS_B); found = 0x7fffffff; }
+  __syncthreads();
+  for (int start = 0; start < nL; start += NT) {
+    const int i = start + tid;
+    double ta = 0.0, tb = 0.0, s = 0.0;
+    if (i < nL) { const unsigned int idx = P.vals[o2 + i]; ta = P.ls_da[o2 + idx]; tb = P.ls_db[o2 + idx]; s = __longlong_as_double((long long)P.keys[o2 + i]); }
+    double ia = ta, ib = tb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ua; ib += ub; }
+    }
+    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+    __syncthreads();
+    double oa = 0.0, ob = 0.0;
+    for (int w = 0; w < warp; w++) { oa += wa[w]; ob += wb[w]; }
+    double ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+    if (lane == 0) { ea = 0.0; eb = 0.0; }
+    const double a_i = carry_a + (oa + ea), b_i = carry_b + (ob + eb);
+    if (i < nL && (a_i * s + b_i > 0)) atomicMin(&found, i);
+    __syncthreads();
+    if (found != 0x7fffffff) {
+      if (i == found) BSC(b, S_TAU) = -b_i / a_i;
+      return;
+    }
+    if (tid == NT - 1) { carry_a += oa + ia; carry_b += ob + ib; }
+    __syncthreads();
+  }
+  if (tid == 0) BSC(b, S_TAU) = -carry_b / carry_a;
+}
+
+__device__ void p_update_iterate(const Args &P, int b) {
+  const int n = P.n, m = P.m;
+  const double tau = BSC(b, S_TAU);
+  const size_t on = (size_t)b * n, om = (size_t)b * m;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const double xi = P.x[on + i];
+    P.x_prev[on + i] = xi; P.x[on + i] = xi + tau * P.d[on + i];
+    const double qd = P.Qd[on + i] * tau;
+    P.Qd[on + i] = qd; P.Qx[on + i] = P.Qx[on + i] + qd;
+  }
+  for (int i = threadIdx.x; i < m; i += NT) {
+    const double ad = P.Ad[om + i] * tau;
+    P.Ad[om + i] = ad; P.Ax[om + i] = P.Ax[om + i] + ad;
+  }
+}
+
+// store_solution (termination.c:242-252) + compute_objective (iteration.c:231-270)
+__device__ void p_store(const Args &P, int b, double *scratch) {
+  const int n = P.n, m = P.m;
+  const BSet &st = P.st;
+  const size_t on = (size_t)b * n, om = (size_t)b * m;
+  const double cinv = P.ctl[b].cinv, inv_gamma = 1 / P.ctl[b].gamma;
+  double obj = 0;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const double xi = P.x[on + i];
+    P.x_out[on + i] = st.scaling ? xi * P.D[i] : xi;
+    if (st.proximal) obj += (0.5 * (P.Qx[on + i] - inv_gamma * xi) + P.q[on + i]) * xi;
+    else obj += (0.5 * P.Qx[on + i] + P.q[on + i]) * xi;
+  }
+  for (int i = threadIdx.x; i < m; i += NT) {
+    double v = P.yh[om + i];
+    if (st.scaling) { v *= cinv; v = v * P.E[i]; }
+    P.y_out[om + i] = v;
+  }
+  obj = block_red<RED_SUM>(obj, scratch);
+  if (threadIdx.x == 0) { if (st.scaling) obj *= cinv; P.ctl[b].objective = obj + st.data_c; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 3) kbp_solve(const Args P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scratch[32];
+  __shared__ int s_b;
+  __shared__ Flags s_f;
+  __shared__ int s_info;
+  Smem S;
+  S.u = smem_raw;
+  S.panel = reinterpret_cast<double *>(smem_raw);
+  S.vs = reinterpret_cast<double *>(smem_raw + kUnionBytes);
+  S.v = S.vs + VS_LEN;
+  S.rd = S.v + NMAX + 16;
+  const int tid = threadIdx.x, n = P.n, m = P.m, ld = P.ld;
+  const BSet &st = P.st;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_b = atomicAdd(P.queue, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= P.nb) return;
+    const size_t on = (size_t)b * n, om = (size_t)b * m;
+    double *Hb = P.H + (size_t)b * P.sLL, *Lb = P.L + (size_t)b * P.sLL, *rdg = P.rdiag + (size_t)b * P.sR;
+    p_init(P, b, scratch);
+    __syncthreads();
+    for (;;) {
+      // ---- residuals + termination scalars ----
+      p_res_m(P, b, scratch);
+      __syncthreads();
+      p_gemv_rows(n, m, n, P.At, P.yh + om, P.Atyh + on, 1.0, S);
+      __syncthreads();
+      p_res_n(P, b, scratch);
+      __syncthreads();
+      if (tid == 0) p_control(P, b, s_f);
+      __syncthreads();
+      const Flags f = s_f;
+      __syncthreads();   // everyone holds a private copy before thread 0 touches s_f again
+      if (f.done) break;
+      // ---- outer updates ----
+      if (f.sigma) { p_update_sigma(P, b, scratch); __syncthreads(); }
+      if (f.outer) { p_outer(P, b, f.outer); __syncthreads(); }
+      if (st.proximal && f.boost) { p_boost(P, b, scratch, S); __syncthreads(); }
+      // ---- inner step ----
+      if (f.inner) {
+        p_lists(P, b, f.refac);
+        __syncthreads();
+        if (f.refac) {
+          const BCtl c = P.ctl[b];
+          if (c.scratch) {
+            for (int idx = tid; idx < n * n; idx += NT) {
+              const int j = idx / n, i = idx - j * n;
+              if (i >= j) Hb[(size_t)i + (size_t)ld * j] = P.Qs[(size_t)i + (size_t)n * j] * c.c;
+            }
+            __syncthreads();
+          }
+          cta_syrk_list(Hb, ld, n, P.At, P.list_pos + om, P.w_pos + om, c.npos, 1.0, S);
+          cta_syrk_list(Hb, ld, n, P.At, P.list_neg + om, P.w_neg + om, c.nneg, -1.0, S);
+        }
+        if (f.factor) {
+          const double beta = P.ctl[b].beta;
+          if (tid == 0) s_info = 0;
+          if (f.fq) cta_potrf(Lb, ld, P.Qs, n, P.ctl[b].c, beta, n, rdg, S, &s_info);
+          else cta_potrf(Lb, ld, Hb, ld, 1.0, beta, n, rdg, S, &s_info);
+        }
+        for (int i = tid; i < n; i += NT) S.v[i] = P.dphi[on + i] * -1;
+        __syncthreads();
+        cta_chol_solve(Lb, ld, n, rdg, S);
+        for (int i = tid; i < n; i += NT) P.d[on + i] = S.v[i];
+        for (int i = tid; i < m; i += NT) P.active_old[om + i] = P.active[om + i];
+        __syncthreads();
+        // ---- line search + iterate update ----
+        p_gemv_rows(n, n, n, P.Qs, P.d + on, P.Qd + on, P.ctl[b].c, S);
+        __syncthreads();
+        p_gemv_cols(n, m, n, P.At, P.d + on, P.Ad + om, S);
+        __syncthreads();
+        p_ls_build(P, b, scratch);
+        __syncthreads();
+        p_sort(2 * m, P.keys + (size_t)b * 2 * m, P.vals + (size_t)b * 2 * m, S);
+        __syncthreads();
+        p_ls_select(P, b);
+        __syncthreads();
+        p_update_iterate(P, b);
+        __syncthreads();
+      }
+      if (tid == 0) {   // end of iteration (qpalm.c:484, 711-735)
+        BCtl &c = P.ctl[b];
+        c.iter++;
+        s_f.done = 0;
+        if (c.iter >= st.max_iter) { c.status = QPALM_MAX_ITER_REACHED; c.done = 1; s_f.done = 1; }
+      }
+      __syncthreads();
+      if (s_f.done) break;
+    }
+    __syncthreads();
+    p_store(P, b, scratch);
+  }
+}
+
+}  // namespace bp
+
+bool batchp_supported(int n, int m) {
+  return n >= 1 && n <= bp::NMAX && m >= 1 && 2 * m <= bp::SORT_MAX && m <= bp::VS_LEN;
+}
+
+int batchp_solve(QPALMB200Batch *B, int nb) {
+  using namespace bp;
+  Engine *e = B->shared;
+  Args P;
+  memset(&P, 0, sizeof(P));
+  P.nb = nb; P.n = B->n; P.m = B->m; P.ld = B->ld; P.st = B->set;
+  P.At = e->At; P.Qs = B->Qs; P.D = e->D; P.Dinv = e->Dinv; P.E = e->E; P.Einv = e->Einv;
+  P.q_raw = B->q_raw; P.bmin_raw = B->bmin_raw; P.bmax_raw = B->bmax_raw; P.x_out = B->x_out; P.y_out = B->y_out;
+  P.q = B->q; P.bmin = B->bmin; P.bmax = B->bmax; P.x = B->x; P.y = B->y; P.Ax = B->Ax; P.Qx = B->Qx; P.Aty = B->Aty;
+  P.x_prev = B->x_prev; P.x0 = B->x0; P.sigma = B->sigma; P.sigma_inv = B->sigma_inv; P.sqrt_sigma = B->sqrt_sigma;
+  P.Axys = B->Axys; P.z = B->z; P.pri_res = B->pri_res; P.pri_res_in = B->pri_res_in; P.yh = B->yh; P.Atyh = B->Atyh;
+  P.df = B->df; P.dphi = B->dphi; P.d = B->d; P.Qd = B->Qd; P.Ad = B->Ad;
+  P.active = B->active; P.active_old = B->active_old; P.active_cand = B->active_cand; P.activeH = B->activeH;
+  P.list_pos = B->list_pos; P.list_neg = B->list_neg; P.sigmaH = B->sigmaH; P.w_pos = B->w_pos; P.w_neg = B->w_neg;
+  P.H = B->H; P.L = B->L; P.rdiag = B->invdiag;
+  P.sLL = (long long)B->ld * B->npad; P.sR = (long long)B->npad * kPanel;
+  P.keys = B->keys; P.vals = B->vals; P.ls_da = B->ls_da; P.ls_db = B->ls_db; P.scal = B->scal; P.ctl = B->ctl; P.queue = B->queue;
+  static int ctas_per_sm = 0, num_sms = 0;
+  if (!ctas_per_sm) {
+    QB_CUDA_TRY(cudaFuncSetAttribute(kbp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    QB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kbp_solve, NT, kSmemBytes));
+    int dev = 0;
+    QB_CUDA_TRY(cudaGetDevice(&dev));
+    QB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  int grid = ctas_per_sm * num_sms;
+  if (grid > nb) grid = nb;
+  QB_CUDA_TRY(cudaMemsetAsync(B->queue, 0, sizeof(int), B->stream));
+  QB_LAUNCH(kbp_solve, grid, NT, kSmemBytes, B->stream, P);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace qb

@@ -14,6 +14,14 @@ def _rel(a, b):
     return np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))) if a.size else 0.0
 
 
+@pytest.fixture(params=["persistent", "lockstep"], autouse=True)
+def engine(request, monkeypatch):
+    """Both batch engines are exercised: the persistent one-CTA-per-instance kernel (batchp.cu, default whenever the
+    shapes fit) and the lock-step engine (batch.cu, any size)."""
+    monkeypatch.setenv("QPALM_B200_BATCH_ENGINE", request.param)
+    return request.param
+
+
 def _check_batch(b, idx, tol=1e-7):
     xs, ys, infos = qb.solve_batch(b)
     for k in idx:
