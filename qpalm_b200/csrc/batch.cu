@@ -786,6 +786,21 @@ __global__ void kb_copy_mask(int nb, const int *src, int *dst) {
   if (b < nb) dst[b] = src[b];
 }
 
+// out (cols x rows, column-major) = in' for in rows x cols column-major
+__global__ void kb_transpose(int rows, int cols, const double *__restrict__ in, double *__restrict__ out) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + threadIdx.x, c = c0 + k;
+    tile[k][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r + (size_t)rows * c] : 0.0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + threadIdx.x, r = r0 + k;
+    if (r < rows && c < cols) out[(size_t)c + (size_t)cols * r] = tile[threadIdx.x][k];
+  }
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -829,6 +844,10 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
     // engine_ruiz_scale applied c = 1/max(1,|D*0|) = 1 to Q, so e->Qd now holds D Q D
   }
   B->Qs = e->Qd;
+  if (m > 0) {   // second layout of the scaled A for the row-parallel A d of the persistent engine
+    if (dev_alloc((void **)&B->Am, sizeof(double) * (size_t)m * n)) { engine_destroy(e); delete B; return nullptr; }
+    QB_LAUNCH(kb_transpose, dim3(cdiv(m, 32), cdiv(n, 32)), dim3(32, 8), 0, e->stream, n, m, e->At, B->Am);
+  }
   const size_t N = n, M = m, NB = nb_max, LL = (size_t)B->ld * B->npad;
   B->wcols = round_up(m > 16 ? m : 16, 16);
   int rc = 0;
@@ -853,6 +872,7 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
     rc |= iv(p, NB);
   rc |= iv(&B->ndone, 4);
   rc |= iv(&B->queue, 4);
+  if (getenv("QPALM_B200_BATCH_PROF")) rc |= dev_alloc((void **)&B->prof, sizeof(long long) * 32 * NB);
   if (const char *env = getenv("QPALM_B200_BATCH_ENGINE")) {   // tests / profiling: force one engine
     if (!strcmp(env, "lockstep")) B->engine = 1; else if (!strcmp(env, "persistent")) B->engine = 2;
   }
@@ -1006,6 +1026,12 @@ extern "C" int qpalm_b200_batch_solve(QPALMB200Batch *B, c_int nb, const c_float
   return 0;
 }
 
+extern "C" int qpalm_b200_batch_phase_profile(QPALMB200Batch *B, c_int nb, long long *out /* nb x 16 */) {
+  if (!B || !B->prof) return 1;
+  QB_CUDA_TRY(cudaMemcpy(out, B->prof, sizeof(long long) * 32 * (size_t)nb, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" long long qpalm_b200_batch_last_launches(const QPALMB200Batch *B) { return B ? B->launches_last : 0; }
 
 extern "C" void qpalm_b200_batch_cleanup(QPALMB200Batch *B) {
@@ -1015,7 +1041,7 @@ extern "C" void qpalm_b200_batch_cleanup(QPALMB200Batch *B) {
                   B->Qd, B->Ad, B->vpad, B->active, B->active_old, B->active_cand, B->activeH, B->list_pos, B->list_neg, B->sigmaH, B->w_pos,
                   B->w_neg, B->Kpos, B->Kneg, B->H, B->L, B->invdiag, B->W, B->keys, B->vals, B->ls_da, B->ls_db, B->scal, B->ctl,
                   B->mask_outer, B->mask_sigma, B->mask_inner, B->mask_refac, B->mask_factor, B->mask_scratch, B->mask_fq, B->mask_boost,
-                  B->ndone, B->info, B->queue};
+                  B->ndone, B->info, B->queue, B->prof, B->Am};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (B->ndone_host) cudaFreeHost(B->ndone_host);
   if (B->ev0) cudaEventDestroy(B->ev0);

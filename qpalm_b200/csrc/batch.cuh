@@ -27,6 +27,7 @@ struct QPALMB200Batch {
   cudaStream_t stream = nullptr;
   qb::BSet set{};
   qb::Engine *shared = nullptr;   // holds the shared, Ruiz-scaled At / Q (dense) and D, E
+  double *Am = nullptr;       // A as m x n column-major (second layout of the shared scaled A, persistent engine)
   double *Qs = nullptr;       // n x n dense full symmetric D Q D (copy of shared->Qd before the c scaling)
   // per-instance arrays [nb][len]
   double *q_raw = nullptr, *bmin_raw = nullptr, *bmax_raw = nullptr, *x_out = nullptr, *y_out = nullptr;
@@ -51,6 +52,7 @@ struct QPALMB200Batch {
   int *queue = nullptr;        // persistent engine: work-queue counter
   int engine = 0;              // 0 auto, 1 lock-step, 2 persistent (QPALM_B200_BATCH_ENGINE)
   int last_engine = 0;
+  long long *prof = nullptr;   // persistent engine: optional per-phase clock totals [nb][16]
 };
 
 namespace qb {

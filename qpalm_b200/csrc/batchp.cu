@@ -43,7 +43,7 @@ constexpr size_t kSmemBytes = kUnionBytes + sizeof(double) * (VS_LEN + NMAX + 16
 struct Args {
   int nb, n, m, ld;
   BSet st;
-  const double *At, *Qs, *D, *Dinv, *E, *Einv;
+  const double *At, *Am, *Qs, *D, *Dinv, *E, *Einv;   // Am: A as m x n column-major (A d row-parallel), At: A' (n x m)
   const double *q_raw, *bmin_raw, *bmax_raw;
   double *x_out, *y_out;
   double *q, *bmin, *bmax, *x, *y, *Ax, *Qx, *Aty, *x_prev, *x0, *sigma, *sigma_inv, *sqrt_sigma, *Axys, *z, *pri_res, *pri_res_in,
@@ -56,6 +56,7 @@ struct Args {
   double *scal;
   BCtl *ctl;
   int *queue;
+  long long *prof;   // optional [nb][16] per-phase clock64 totals (QPALM_B200_BATCH_PROF=1)
 };
 
 struct Flags { int outer, sigma, inner, refac, factor, fq, boost, done; };
@@ -73,7 +74,7 @@ struct Smem {
 // ------------------------------------------------------------------------------------------------
 #define RED_OUT(op, val, slot) { const double r_ = block_red<op>(val, scratch); if (threadIdx.x == 0) BSC(b, slot) = r_; }
 
-__device__ void p_init(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_init(const Args &P, int b, double *scratch) {
   __shared__ double cc_s, sig_s;
   const int n = P.n, m = P.m, tid = threadIdx.x;
   const BSet &st = P.st;
@@ -121,7 +122,7 @@ __device__ void p_init(const Args &P, int b, double *scratch) {
 }
 
 // compute_residuals (iteration.c:24-48) + candidate active set (newton.c:122-149) + m-side termination reductions
-__device__ void p_res_m(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_res_m(const Args &P, int b, double *scratch) {
   const int m = P.m, scaling = P.st.scaling;
   const size_t om = (size_t)b * m;
   double r_pri = 0, r_raw = 0, r_ax = 0, r_z = 0, r_edy = 0, oob = 0, adx_max = -1.0e300, adx_min = 1.0e300;
@@ -157,49 +158,82 @@ __device__ void p_res_m(const Args &P, int b, double *scratch) {
   RED_OUT(RED_SUM, n_ent, S_NB_ENTER) RED_OUT(RED_SUM, n_lea, S_NB_LEAVE)
 }
 
-// out[i] = scale * sum_k M[i + ld*k] v[k], i < nrows (row sums of a shared column-major matrix: A'yh and Q d).
-// The rows are split over NT / 128-row groups: with nrows <= 128 two thread groups each take half of the columns.
-__device__ void p_gemv_rows(int nrows, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v,
-                            double *out, double scale, const Smem &S) {
+// out[i] = scale * sum_k M[i + ld*k] v[k], i < nrows (row sums of a shared column-major matrix: A'yh, Q d and, with the
+// m x n copy of A, A d).  Each thread owns up to 4 rows (i, i + NT, ...) and walks the columns with 4-way unrolling, so
+// 16 independent L2 requests are in flight per thread; per-row summation order is fixed (reproducible).
+template <int RP, int KU>
+__device__ __forceinline__ void gemv_rows_body(int nrows, int ncols, int ld, const double *__restrict__ M, double *out, double scale,
+                                               const double *vs) {
   const int tid = threadIdx.x;
-  for (int k = tid; k < ncols; k += NT) S.vs[k] = v[k];
-  __syncthreads();
-  for (int i = tid; i < nrows; i += NT) {
-    const double *r = M + i;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  for (int i0 = tid; i0 < nrows; i0 += RP * NT) {
+    int ri[RP];
+#pragma unroll
+    for (int a = 0; a < RP; a++) { ri[a] = i0 + a * NT; if (ri[a] >= nrows) ri[a] = nrows - 1; }
+    double acc[RP][KU];
+#pragma unroll
+    for (int a = 0; a < RP; a++)
+#pragma unroll
+      for (int u = 0; u < KU; u++) acc[a][u] = 0.0;
     int k = 0;
-    for (; k + 7 < ncols; k += 8) {
-      a0 = fma(r[(size_t)k * ld], S.vs[k], a0);
-      a1 = fma(r[(size_t)(k + 1) * ld], S.vs[k + 1], a1);
-      a2 = fma(r[(size_t)(k + 2) * ld], S.vs[k + 2], a2);
-      a3 = fma(r[(size_t)(k + 3) * ld], S.vs[k + 3], a3);
-      a4 = fma(r[(size_t)(k + 4) * ld], S.vs[k + 4], a4);
-      a5 = fma(r[(size_t)(k + 5) * ld], S.vs[k + 5], a5);
-      a6 = fma(r[(size_t)(k + 6) * ld], S.vs[k + 6], a6);
-      a7 = fma(r[(size_t)(k + 7) * ld], S.vs[k + 7], a7);
+    for (; k + KU - 1 < ncols; k += KU) {
+#pragma unroll
+      for (int u = 0; u < KU; u++) {
+        const double vk = vs[k + u];
+        const double *col = M + (size_t)(k + u) * ld;
+#pragma unroll
+        for (int a = 0; a < RP; a++) acc[a][u] = fma(col[ri[a]], vk, acc[a][u]);
+      }
     }
-    for (; k < ncols; k++) a0 = fma(r[(size_t)k * ld], S.vs[k], a0);
-    out[i] = (((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))) * scale;
+    for (; k < ncols; k++) {
+      const double vk = vs[k];
+      const double *col = M + (size_t)k * ld;
+#pragma unroll
+      for (int a = 0; a < RP; a++) acc[a][0] = fma(col[ri[a]], vk, acc[a][0]);
+    }
+#pragma unroll
+    for (int a = 0; a < RP; a++) {
+      double t = 0.0;
+#pragma unroll
+      for (int u = KU - 1; u >= 0; u--) t += acc[a][u];
+      if (i0 + a * NT < nrows) out[i0 + a * NT] = t * scale;
+    }
   }
 }
+__device__ __forceinline__ void p_gemv_rows(int nrows, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v,
+                                            double *out, double scale, const Smem &S) {
+  for (int k = threadIdx.x; k < ncols; k += NT) S.vs[k] = v[k];
+  __syncthreads();
+  if (nrows <= NT) gemv_rows_body<1, 8>(nrows, ncols, ld, M, out, scale, S.vs);    // one row per thread, 8 columns in flight
+  else gemv_rows_body<4, 4>(nrows, ncols, ld, M, out, scale, S.vs);               // 4 rows x 4 columns in flight
+}
 // out[k] = sum_i M[i + ld*k] v[i], k < ncols (column dots: A d with A' as M); one warp per column
-__device__ void p_gemv_cols(int len, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v, double *out,
+__device__ __forceinline__ void p_gemv_cols(int len, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v, double *out,
                             const Smem &S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k = tid; k < len; k += NT) S.vs[k] = v[k];
   __syncthreads();
-  for (int col = warp; col < ncols; col += NW) {
-    const double *c = M + (size_t)col * ld;
-    double a0 = 0, a1 = 0;
-    int i = lane;
-    for (; i + 32 < len; i += 64) { a0 = fma(c[i], S.vs[i], a0); a1 = fma(c[i + 32], S.vs[i + 32], a1); }
-    for (; i < len; i += 32) a0 = fma(c[i], S.vs[i], a0);
-    const double acc = warp_sum(a0 + a1);
-    if (lane == 0) out[col] = acc;
+  // four columns per warp step: their loads are independent, so 4 x len/32 L2 requests are in flight per lane
+  for (int col0 = warp * 4; col0 < ncols; col0 += NW * 4) {
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int col = (col0 + u < ncols) ? col0 + u : ncols - 1;
+      const double *c = M + (size_t)col * ld;
+      double a0 = 0, a1 = 0;
+      int i = lane;
+      for (; i + 32 < len; i += 64) { a0 = fma(c[i], S.vs[i], a0); a1 = fma(c[i + 32], S.vs[i + 32], a1); }
+      for (; i < len; i += 32) a0 = fma(c[i], S.vs[i], a0);
+      acc[u] = a0 + a1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const double r = warp_sum(acc[u]);
+      if (lane == 0 && col0 + u < ncols) out[col0 + u] = r;
+    }
   }
 }
 
-__device__ void p_res_n(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_res_n(const Args &P, int b, double *scratch) {
   const int n = P.n;
   const BSet &st = P.st;
   const size_t on = (size_t)b * n;
@@ -235,7 +269,7 @@ __device__ void p_res_n(const Args &P, int b, double *scratch) {
 }
 
 // the control flow of qpalm_solve for one iteration (src/qpalm.c:484-711), executed by one thread
-__device__ void p_control(const Args &P, int b, Flags &f) {
+__device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
   const BSet &st = P.st;
   const int n = P.n, m = P.m;
   f.outer = f.sigma = f.inner = f.refac = f.factor = f.fq = f.boost = f.done = 0;
@@ -308,7 +342,7 @@ __device__ void p_control(const Args &P, int b, Flags &f) {
 
 // update_sigma (iteration.c:86-145); every sigma change leads to a refactorisation (same matrix as the reference's
 // rank update of solver_interface.c:443-503)
-__device__ void p_update_sigma(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_update_sigma(const Args &P, int b, double *scratch) {
   const int m = P.m;
   const BSet &st = P.st;
   const size_t om = (size_t)b * m;
@@ -360,7 +394,9 @@ __device__ void p_outer(const Args &P, int b, int kind) {
 // ------------------------------------------------------------------------------------------------
 // dst(i, j) = [first ? sscale * src(i, j) + (i == j) * diag_add : dst(i, j)] + sign * sum_{c < w} U[c][i - u0] U[c][j - u0]
 // for r0 <= j <= i < n.  U is PW x LDP in shared memory.  Warp task = 128 rows x 4 columns, 4 x 4 register block per lane.
-__device__ void cta_rank_update_lower(double *dst, int ldd, const double *src, int lds, double sscale, double diag_add, bool first,
+// The accumulators START from the old values: all 16 global loads of a task are issued up front and their latency is
+// paid once per task (a read-modify-write after the loop serialises 16 dependent L2 round trips: measured 6x slower).
+__device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, const double *src, int lds, double sscale, double diag_add, bool first,
                                       int r0, int n, const double *U, int u0, int w, double sign) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rem = n - r0;
@@ -371,21 +407,28 @@ __device__ void cta_rank_update_lower(double *dst, int ldd, const double *src, i
     const int i0 = r0 + ib * 128, j0 = r0 + jb * 4;
     if (i0 + 127 < j0) continue;   // block entirely above the diagonal
     double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) acc[a][e] = 0.0;
-    int ri[4];
+    int ri[4], cj[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) { ri[a] = i0 + lane + 32 * a; if (ri[a] >= n) ri[a] = n - 1; }
-    int cj[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) { cj[e] = j0 + e; if (cj[e] >= n) cj[e] = n - 1; }
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int i = i0 + lane + 32 * a, j = j0 + e;
+        double base = 0.0;
+        if (i < n && j < n && i >= j) {
+          if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
+          else base = dst[(size_t)i + (size_t)ldd * j];
+        }
+        acc[a][e] = base;
+      }
     for (int c = 0; c < w; c++) {
       const double *Uc = U + c * LDP - u0;
       double ua[4], ub[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) ua[a] = Uc[ri[a]];
+      for (int a = 0; a < 4; a++) ua[a] = sign * Uc[ri[a]];
 #pragma unroll
       for (int e = 0; e < 4; e++) ub[e] = Uc[cj[e]];
 #pragma unroll
@@ -394,53 +437,120 @@ __device__ void cta_rank_update_lower(double *dst, int ldd, const double *src, i
         for (int e = 0; e < 4; e++) acc[a][e] = fma(ua[a], ub[e], acc[a][e]);
     }
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int j = j0 + e;
-      if (j >= n) continue;
+    for (int e = 0; e < 4; e++)
 #pragma unroll
       for (int a = 0; a < 4; a++) {
-        const int i = i0 + lane + 32 * a;
-        if (i >= n || i < j) continue;
-        double base;
-        if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
-        else base = dst[(size_t)i + (size_t)ldd * j];
-        dst[(size_t)i + (size_t)ldd * j] = base + sign * acc[a][e];
+        const int i = i0 + lane + 32 * a, j = j0 + e;
+        if (i < n && j < n && i >= j) dst[(size_t)i + (size_t)ldd * j] = acc[a][e];
       }
-    }
   }
 }
 
-// Cholesky of the w x w diagonal block held in the panel (rows/cols 0..w-1 of P[t][r]); warp 0 only.  Rows >= w act
-// as identity rows so that the 32-wide register code needs no special cases.  rd[j] = 1 / l_jj.
-__device__ void warp_factor_diag(double *Pn, double *rd, int w, int *info) {
+// The PW = 32 column panel is factorised as two 16-column sub-panels so that every per-thread register array is 16
+// doubles (a 32-wide version needs 64 registers per array and spills at 3 CTAs / SM).
+constexpr int SW = 16;
+
+// Cholesky of the 16 x 16 block at (c0, c0) of the panel (P[t][r], t = column, r = row), warp 0, in place in shared
+// memory with ROLLED loops: a fully unrolled register version is ~3.4k straight-line instructions that one warp executes
+// once per call, i.e. it runs at instruction-fetch speed (measured 19 us per block vs ~3 us for this form).
+// Columns/rows >= w (ragged last panel) are skipped.  rd[c0 + j] = 1 / l_jj.
+__device__ __forceinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, int w, int *info) {
   const int lane = threadIdx.x & 31;
-  double a[PW];
-#pragma unroll
-  for (int c = 0; c < PW; c++) a[c] = (lane < w && c < w) ? ((c <= lane) ? Pn[c * LDP + lane] : 0.0) : ((c == lane) ? 1.0 : 0.0);
+  const int row = c0 + lane;
+  const int wend = (w - c0 < SW) ? w - c0 : SW;   // live columns of this block
+  const bool live = lane < wend;
   bool bad = false;
-#pragma unroll
-  for (int j = 0; j < PW; j++) {
-    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+#pragma unroll 1
+  for (int j = 0; j < wend; j++) {
+    const double pjj = Pn[(c0 + j) * LDP + c0 + j];
+    __syncwarp();   // every lane holds the pivot before lane j overwrites it
     if (!(pjj > 0.0)) bad = true;
-    const double ljj = sqrt(pjj), inv = 1.0 / ljj;
-    if (lane == j) { a[j] = ljj; rd[j] = inv; }
-    else if (lane > j) a[j] *= inv;
+    const double inv = rsqrt(pjj), ljj = pjj * inv;
+    double l = 0.0;
+    if (live && lane > j) { l = Pn[(c0 + j) * LDP + row] * inv; Pn[(c0 + j) * LDP + row] = l; }
+    else if (lane == j) { Pn[(c0 + j) * LDP + row] = ljj; rd[c0 + j] = inv; }
+    __syncwarp();
+    // rank-1 update of the remaining columns: the 15 column updates are independent, so the inner loop is unrolled with
+    // a run-time predicate (the outer loop stays rolled: compact code, see above)
 #pragma unroll
-    for (int c = j + 1; c < PW; c++) {
-      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-      if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
+    for (int c = 1; c < SW; c++) {
+      if (c > j && c < wend && lane >= c && live)
+        Pn[(c0 + c) * LDP + row] = fma(-l, Pn[(c0 + j) * LDP + c0 + c], Pn[(c0 + c) * LDP + row]);
     }
+    __syncwarp();
   }
-#pragma unroll
-  for (int c = 0; c < PW; c++) if (c <= lane && lane < w) Pn[c * LDP + lane] = a[c];
   if (bad && lane == 0 && info) *info = 1;
 }
 
+// rows r >= c0 + 16 of the panel: P[c0 + c][r] <- forward substitution against the 16 x 16 factor at (c0, c0)
+__device__ __forceinline__ void panel_solve16(double *Pn, const double *rd, int c0, int w, int rows) {
+  for (int r = c0 + SW + threadIdx.x; r < rows; r += NT) {
+    double v[SW];
+#pragma unroll
+    for (int c = 0; c < SW; c++) v[c] = (c0 + c < w) ? Pn[(c0 + c) * LDP + r] : 0.0;
+#pragma unroll
+    for (int c = 0; c < SW; c++) {
+      if (c0 + c < w) {
+        double s = v[c];
+#pragma unroll
+        for (int t = 0; t < SW; t++) if (t < c) s = fma(-v[t], Pn[(c0 + t) * LDP + c0 + c], s);
+        v[c] = s * rd[c0 + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < SW; c++) if (c0 + c < w) Pn[(c0 + c) * LDP + r] = v[c];
+  }
+}
+
+// rows r >= 16: P[16 + c][r] -= sum_{t < 16} P[t][r] P[t][16 + c]  for 16 + c <= min(r, w - 1)
+__device__ __forceinline__ void panel_update16(double *Pn, int w, int rows) {
+  for (int r = SW + threadIdx.x; r < rows; r += NT) {
+    double acc[SW];
+#pragma unroll
+    for (int c = 0; c < SW; c++) acc[c] = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < SW; t++) {
+      const double lr = Pn[t * LDP + r];
+#pragma unroll
+      for (int c = 0; c < SW; c++) acc[c] = fma(lr, Pn[t * LDP + SW + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < SW; c++) if (SW + c < w && SW + c <= r) Pn[(SW + c) * LDP + r] -= acc[c];
+  }
+}
+
 // L <- chol(sscale * src + beta I) (lower, n x n), right-looking with PW-column panels.  rdiag_g[j] = 1 / l_jj.
-__device__ void cta_potrf(double *L, int ld, const double *src, int lds, double sscale, double beta, int n, double *rdiag_g,
-                          const Smem &S, int *info) {
+// forward substitution step of one resident panel: z_k = L_kk^{-1} v_k (warp 0), v_below -= L_below,k z_k (all threads)
+__device__ __forceinline__ void panel_forward(const double *Pn, double *v, const double *rdv, int k0, int w, int rows) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    double vl = (lane < w) ? v[k0 + lane] : 0.0;
+    const double rd = (lane < w) ? rdv[lane] : 1.0;
+    for (int j = 0; j < w; j++) {
+      const double zj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
+      if (lane == j) vl = zj;
+      else if (lane > j && lane < w) vl = fma(-Pn[j * LDP + lane], zj, vl);
+    }
+    if (lane < w) v[k0 + lane] = vl;
+  }
+  __syncthreads();
+  for (int r = w + tid; r < rows; r += NT) {
+    double s0 = 0.0, s1 = 0.0;
+    int t = 0;
+    for (; t + 1 < w; t += 2) { s0 = fma(Pn[t * LDP + r], v[k0 + t], s0); s1 = fma(Pn[(t + 1) * LDP + r], v[k0 + t + 1], s1); }
+    if (t < w) s0 = fma(Pn[t * LDP + r], v[k0 + t], s0);
+    v[k0 + r] -= (s0 + s1);
+  }
+  __syncthreads();
+}
+
+// fwd: additionally run the forward substitution L z = v on S.v while each panel is resident (saves re-reading L).
+__device__ __forceinline__ void cta_potrf(double *L, int ld, const double *src, int lds, double sscale, double beta, int n, double *rdiag_g,
+                          const Smem &S, int *info, bool fwd, long long *pf) {
   const int tid = threadIdx.x;
   double *Pn = S.panel;
+  long long tq = clock64();
+#define PQ(k) do { if (pf && tid == 0) { const long long t_ = clock64(); pf[k] += t_ - tq; tq = t_; } } while (0)
   for (int k0 = 0; k0 < n; k0 += PW) {
     const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
     const bool first = (k0 == 0);
@@ -455,66 +565,56 @@ __device__ void cta_potrf(double *L, int ld, const double *src, int lds, double 
       Pn[t * LDP + r] = v;
     }
     __syncthreads();
-    if (tid < 32) warp_factor_diag(Pn, S.rd, w, info);
+    PQ(16);
+    if (tid < 32) warp_factor_diag16(Pn, S.rd, 0, w, info);
     __syncthreads();
-    for (int r = w + tid; r < rows; r += NT) {   // rows below the diagonal block: forward substitution, one row per thread
-      double v[PW];
-#pragma unroll
-      for (int c = 0; c < PW; c++) v[c] = (c < w) ? Pn[c * LDP + r] : 0.0;
-#pragma unroll
-      for (int c = 0; c < PW; c++) {
-        if (c < w) {
-          double s = v[c];
-#pragma unroll
-          for (int t = 0; t < c; t++) s = fma(-v[t], Pn[t * LDP + c], s);
-          v[c] = s * S.rd[c];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < PW; c++) if (c < w) Pn[c * LDP + r] = v[c];
+    PQ(17);
+    panel_solve16(Pn, S.rd, 0, w, rows);
+    __syncthreads();
+    PQ(18);
+    if (w > SW) {
+      panel_update16(Pn, w, rows);
+      __syncthreads();
+      PQ(19);
+      if (tid < 32) warp_factor_diag16(Pn, S.rd, SW, w, info);
+      __syncthreads();
+      PQ(17);
+      panel_solve16(Pn, S.rd, SW, w, rows);
+      __syncthreads();
+      PQ(18);
     }
-    __syncthreads();
     for (int idx = tid; idx < w * rows; idx += NT) {   // final columns of L
       const int t = idx / rows, r = idx - t * rows;
       if (r >= t) L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] = Pn[t * LDP + r];
     }
     if (tid < w) rdiag_g[k0 + tid] = S.rd[tid];
+    if (fwd) {
+      panel_forward(Pn, S.v, S.rd, k0, w, rows);   // ends with a barrier; only reads the panel
+    }
+    PQ(20);
     cta_rank_update_lower(L, ld, src, lds, sscale, beta, first, k0 + w, n, Pn, k0, w, -1.0);
     __syncthreads();
+    PQ(21);
   }
+#undef PQ
 }
 
-// v <- (L L')^{-1} v, v in shared memory (S.v), L n x n lower in global memory, rdiag_g = 1 / diag(L)
-__device__ void cta_chol_solve(const double *L, int ld, int n, const double *rdiag_g, const Smem &S) {
+// v <- (L L')^{-1} v, v in shared memory (S.v), L n x n lower in global memory, rdiag_g = 1 / diag(L).
+// skip_forward: the forward substitution was already done inside cta_potrf.
+__device__ __forceinline__ void cta_chol_solve(const double *L, int ld, int n, const double *rdiag_g, const Smem &S, bool skip_forward) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *Pn = S.panel, *v = S.v;
-  // forward: L z = v
-  for (int k0 = 0; k0 < n; k0 += PW) {
-    const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
-    for (int idx = tid; idx < w * rows; idx += NT) {
-      const int t = idx / rows, r = idx - t * rows;
-      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double vl = (lane < w) ? v[k0 + lane] : 0.0;
-      const double rd = (lane < w) ? rdiag_g[k0 + lane] : 1.0;
-      for (int j = 0; j < w; j++) {
-        const double zj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
-        if (lane == j) vl = zj;
-        else if (lane > j && lane < w) vl = fma(-Pn[j * LDP + lane], zj, vl);
+  if (!skip_forward) {
+    for (int k0 = 0; k0 < n; k0 += PW) {   // forward: L z = v
+      const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
+      for (int idx = tid; idx < w * rows; idx += NT) {
+        const int t = idx / rows, r = idx - t * rows;
+        Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
       }
-      if (lane < w) v[k0 + lane] = vl;
+      if (tid < w) S.rd[tid] = rdiag_g[k0 + tid];
+      __syncthreads();
+      panel_forward(Pn, v, S.rd, k0, w, rows);
     }
-    __syncthreads();
-    for (int r = w + tid; r < rows; r += NT) {
-      double s0 = 0.0, s1 = 0.0;
-      int t = 0;
-      for (; t + 1 < w; t += 2) { s0 = fma(Pn[t * LDP + r], v[k0 + t], s0); s1 = fma(Pn[(t + 1) * LDP + r], v[k0 + t + 1], s1); }
-      if (t < w) s0 = fma(Pn[t * LDP + r], v[k0 + t], s0);
-      v[k0 + r] -= (s0 + s1);
-    }
-    __syncthreads();
   }
   // backward: L' d = z
   const int last = ((n - 1) / PW) * PW;
@@ -547,7 +647,7 @@ __device__ void cta_chol_solve(const double *L, int ld, int n, const double *rdi
 }
 
 // dst(lower) += sign * sum_{c < cnt} (wgt[c] A'[:, list[c]]) (...)'   in chunks of PW list entries staged in the panel
-__device__ void cta_syrk_list(double *dst, int ld, int n, const double *__restrict__ At, const int *__restrict__ list,
+__device__ __forceinline__ void cta_syrk_list(double *dst, int ld, int n, const double *__restrict__ At, const int *__restrict__ list,
                               const double *__restrict__ wgt, int cnt, double sign, const Smem &S) {
   const int tid = threadIdx.x;
   for (int off = 0; off < cnt; off += PW) {
@@ -565,7 +665,7 @@ __device__ void cta_syrk_list(double *dst, int ld, int n, const double *__restri
 // ------------------------------------------------------------------------------------------------
 // active-set commit + ordered H-difference lists (batch.cu kb_lists, one CTA)
 // ------------------------------------------------------------------------------------------------
-__device__ void p_lists(const Args &P, int b, int refac) {
+__device__ __noinline__ void p_lists(const Args &P, int b, int refac) {
   __shared__ int warp_cnt0[NW], warp_cnt1[NW];
   __shared__ int base0, base1, redo;
   const int m = P.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -615,7 +715,7 @@ __device__ void p_lists(const Args &P, int b, int refac) {
 }
 
 // ordered list of the active rows with weights sqrt(sigma) (boost_gamma's A_J' Sigma_J A_J)
-__device__ void p_active_list(const Args &P, int b) {
+__device__ __noinline__ void p_active_list(const Args &P, int b) {
   __shared__ int warp_cnt[NW];
   __shared__ int base;
   const int m = P.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -639,7 +739,7 @@ __device__ void p_active_list(const Args &P, int b) {
 }
 
 // boost_gamma path of the outer update (qpalm.c:613-627, iteration.c:159-211).  Returns with gamma / reset_newton set.
-__device__ void p_boost(const Args &P, int b, double *scratch, const Smem &S) {
+__device__ __noinline__ void p_boost(const Args &P, int b, double *scratch, const Smem &S) {
   __shared__ int need_gersh;
   const int n = P.n, m = P.m, tid = threadIdx.x;
   const BSet &st = P.st;
@@ -707,7 +807,7 @@ __device__ void p_boost(const Args &P, int b, double *scratch, const Smem &S) {
 // ------------------------------------------------------------------------------------------------
 // line search (linesearch.c:14-120)
 // ------------------------------------------------------------------------------------------------
-__device__ void p_ls_build(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_ls_build(const Args &P, int b, double *scratch) {
   const int n = P.n, m = P.m;
   const size_t on = (size_t)b * n, om = (size_t)b * m, o2 = (size_t)b * 2 * m;
   const double inv_gamma = 1 / P.ctl[b].gamma;
@@ -745,7 +845,7 @@ __device__ void p_ls_build(const Args &P, int b, double *scratch) {
 }
 
 // stable LSD radix sort of N <= SORT_MAX (key, val) pairs in shared memory; sorted pairs are written back to global
-__device__ void p_sort(int N, unsigned long long *kg, unsigned int *vg, const Smem &S) {
+__device__ __forceinline__ void p_sort(int N, unsigned long long *kg, unsigned int *vg, const Smem &S) {
   unsigned long long *k0 = reinterpret_cast<unsigned long long *>(S.u), *k1 = k0 + SORT_MAX;
   unsigned int *v0 = reinterpret_cast<unsigned int *>(k1 + SORT_MAX), *v1 = v0 + SORT_MAX;
   unsigned int *warp_cnt = v1 + SORT_MAX;            // [NW][256]
@@ -807,7 +907,7 @@ __device__ void p_sort(int N, unsigned long long *kg, unsigned int *vg, const Sm
   for (int i = tid; i < N; i += NT) { kg[i] = kin[i]; vg[i] = vin[i]; }
 }
 
-__device__ void p_ls_select(const Args &P, int b) {
+__device__ __noinline__ void p_ls_select(const Args &P, int b) {
   __shared__ double wa[NW], wb[NW];
   __shared__ double carry_a, carry_b;
   __shared__ int found;
@@ -862,7 +962,7 @@ __device__ void p_update_iterate(const Args &P, int b) {
 }
 
 // store_solution (termination.c:242-252) + compute_objective (iteration.c:231-270)
-__device__ void p_store(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_store(const Args &P, int b, double *scratch) {
   const int n = P.n, m = P.m;
   const BSet &st = P.st;
   const size_t on = (size_t)b * n, om = (size_t)b * m;
@@ -886,6 +986,7 @@ __device__ void p_store(const Args &P, int b, double *scratch) {
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
+#define PH(k) do { if (P.prof && tid == 0) { const long long t_ = clock64(); P.prof[(size_t)b * 32 + (k)] += t_ - t_ph; t_ph = t_; } } while (0)
 __global__ void __launch_bounds__(NT, 3) kbp_solve(const Args P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[32];
@@ -908,29 +1009,37 @@ __global__ void __launch_bounds__(NT, 3) kbp_solve(const Args P) {
     if (b >= P.nb) return;
     const size_t on = (size_t)b * n, om = (size_t)b * m;
     double *Hb = P.H + (size_t)b * P.sLL, *Lb = P.L + (size_t)b * P.sLL, *rdg = P.rdiag + (size_t)b * P.sR;
+    long long t_ph = clock64();
+    if (P.prof && tid == 0) for (int k = 0; k < 32; k++) P.prof[(size_t)b * 32 + k] = 0;
     p_init(P, b, scratch);
     __syncthreads();
+    PH(0);
     for (;;) {
       // ---- residuals + termination scalars ----
       p_res_m(P, b, scratch);
       __syncthreads();
+      PH(1);
       p_gemv_rows(n, m, n, P.At, P.yh + om, P.Atyh + on, 1.0, S);
       __syncthreads();
+      PH(2);
       p_res_n(P, b, scratch);
       __syncthreads();
       if (tid == 0) p_control(P, b, s_f);
       __syncthreads();
       const Flags f = s_f;
       __syncthreads();   // everyone holds a private copy before thread 0 touches s_f again
+      PH(3);
       if (f.done) break;
       // ---- outer updates ----
       if (f.sigma) { p_update_sigma(P, b, scratch); __syncthreads(); }
       if (f.outer) { p_outer(P, b, f.outer); __syncthreads(); }
       if (st.proximal && f.boost) { p_boost(P, b, scratch, S); __syncthreads(); }
+      PH(4);
       // ---- inner step ----
       if (f.inner) {
         p_lists(P, b, f.refac);
         __syncthreads();
+        PH(5);
         if (f.refac) {
           const BCtl c = P.ctl[b];
           if (c.scratch) {
@@ -940,34 +1049,43 @@ __global__ void __launch_bounds__(NT, 3) kbp_solve(const Args P) {
             }
             __syncthreads();
           }
-          cta_syrk_list(Hb, ld, n, P.At, P.list_pos + om, P.w_pos + om, c.npos, 1.0, S);
-          cta_syrk_list(Hb, ld, n, P.At, P.list_neg + om, P.w_neg + om, c.nneg, -1.0, S);
+          for (int pass = 0; pass < 2; pass++)   // + entering / grown sigma, then - leaving (one inlined copy of the SYRK)
+            cta_syrk_list(Hb, ld, n, P.At, (pass ? P.list_neg : P.list_pos) + om, (pass ? P.w_neg : P.w_pos) + om,
+                          pass ? c.nneg : c.npos, pass ? -1.0 : 1.0, S);
         }
+        PH(6);
+        for (int i = tid; i < n; i += NT) S.v[i] = P.dphi[on + i] * -1;
+        __syncthreads();
         if (f.factor) {
           const double beta = P.ctl[b].beta;
           if (tid == 0) s_info = 0;
-          if (f.fq) cta_potrf(Lb, ld, P.Qs, n, P.ctl[b].c, beta, n, rdg, S, &s_info);
-          else cta_potrf(Lb, ld, Hb, ld, 1.0, beta, n, rdg, S, &s_info);
+          cta_potrf(Lb, ld, f.fq ? P.Qs : Hb, f.fq ? n : ld, f.fq ? P.ctl[b].c : 1.0, beta, n, rdg, S, &s_info, true,
+                    P.prof ? P.prof + (size_t)b * 32 : nullptr);
         }
-        for (int i = tid; i < n; i += NT) S.v[i] = P.dphi[on + i] * -1;
-        __syncthreads();
-        cta_chol_solve(Lb, ld, n, rdg, S);
+        PH(7);
+        cta_chol_solve(Lb, ld, n, rdg, S, f.factor != 0);
         for (int i = tid; i < n; i += NT) P.d[on + i] = S.v[i];
         for (int i = tid; i < m; i += NT) P.active_old[om + i] = P.active[om + i];
         __syncthreads();
+        PH(8);
         // ---- line search + iterate update ----
         p_gemv_rows(n, n, n, P.Qs, P.d + on, P.Qd + on, P.ctl[b].c, S);
         __syncthreads();
-        p_gemv_cols(n, m, n, P.At, P.d + on, P.Ad + om, S);
+        PH(13);
+        p_gemv_rows(m, n, m, P.Am, P.d + on, P.Ad + om, 1.0, S);
         __syncthreads();
+        PH(9);
         p_ls_build(P, b, scratch);
         __syncthreads();
+        PH(10);
         p_sort(2 * m, P.keys + (size_t)b * 2 * m, P.vals + (size_t)b * 2 * m, S);
         __syncthreads();
+        PH(11);
         p_ls_select(P, b);
         __syncthreads();
         p_update_iterate(P, b);
         __syncthreads();
+        PH(12);
       }
       if (tid == 0) {   // end of iteration (qpalm.c:484, 711-735)
         BCtl &c = P.ctl[b];
@@ -995,7 +1113,7 @@ int batchp_solve(QPALMB200Batch *B, int nb) {
   Args P;
   memset(&P, 0, sizeof(P));
   P.nb = nb; P.n = B->n; P.m = B->m; P.ld = B->ld; P.st = B->set;
-  P.At = e->At; P.Qs = B->Qs; P.D = e->D; P.Dinv = e->Dinv; P.E = e->E; P.Einv = e->Einv;
+  P.At = e->At; P.Am = B->Am; P.Qs = B->Qs; P.D = e->D; P.Dinv = e->Dinv; P.E = e->E; P.Einv = e->Einv;
   P.q_raw = B->q_raw; P.bmin_raw = B->bmin_raw; P.bmax_raw = B->bmax_raw; P.x_out = B->x_out; P.y_out = B->y_out;
   P.q = B->q; P.bmin = B->bmin; P.bmax = B->bmax; P.x = B->x; P.y = B->y; P.Ax = B->Ax; P.Qx = B->Qx; P.Aty = B->Aty;
   P.x_prev = B->x_prev; P.x0 = B->x0; P.sigma = B->sigma; P.sigma_inv = B->sigma_inv; P.sqrt_sigma = B->sqrt_sigma;
@@ -1005,6 +1123,7 @@ int batchp_solve(QPALMB200Batch *B, int nb) {
   P.list_pos = B->list_pos; P.list_neg = B->list_neg; P.sigmaH = B->sigmaH; P.w_pos = B->w_pos; P.w_neg = B->w_neg;
   P.H = B->H; P.L = B->L; P.rdiag = B->invdiag;
   P.sLL = (long long)B->ld * B->npad; P.sR = (long long)B->npad * kPanel;
+  P.prof = B->prof;
   P.keys = B->keys; P.vals = B->vals; P.ls_da = B->ls_da; P.ls_db = B->ls_db; P.scal = B->scal; P.ctl = B->ctl; P.queue = B->queue;
   static int ctas_per_sm = 0, num_sms = 0;
   if (!ctas_per_sm) {

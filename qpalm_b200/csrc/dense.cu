@@ -192,10 +192,14 @@ __device__ void factor32_warp(double *As, double *rdiag, int base, int lane, int
     const double ljj = sqrt(pjj), inv = 1.0 / ljj;
     if (lane == j) { a[j] = ljj; rdiag[base + j] = inv; }
     else if (lane > j) a[j] *= inv;
+    // constant inner bounds + predicate (a j-dependent bound is unrolled before the outer loop and leaves a[] in
+    // local memory); the dead half folds away after the outer unroll
 #pragma unroll
-    for (int c = j + 1; c < SB; c++) {
-      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-      if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
+    for (int c = 0; c < SB; c++) {
+      if (c > j) {
+        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+        if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
+      }
     }
   }
 #pragma unroll
@@ -213,7 +217,7 @@ __device__ void panel_solve(double *As, const double *rdiag, int base, int tid) 
   for (int c = 0; c < SB; c++) {
     double s = v[c];
 #pragma unroll
-    for (int t = 0; t < c; t++) s = fma(-v[t], As[(base + c) * DS + base + t], s);
+    for (int t = 0; t < SB; t++) if (t < c) s = fma(-v[t], As[(base + c) * DS + base + t], s);
     v[c] = s * rdiag[base + c];
   }
 #pragma unroll
@@ -242,7 +246,7 @@ __device__ void inv32_warp(const double *As, double *Xs, const double *rdiag, in
   for (int r = 0; r < SB; r++) {
     double s = 0.0;
 #pragma unroll
-    for (int t = 0; t < r; t++) s = fma(As[(base + r) * DS + base + t], x[t], s);   // x[t] == 0 for t < lane
+    for (int t = 0; t < SB; t++) if (t < r) s = fma(As[(base + r) * DS + base + t], x[t], s);   // x[t] == 0 for t < lane
     x[r] = (r < lane) ? 0.0 : ((r == lane) ? rdiag[base + r] : -s * rdiag[base + r]);
   }
 #pragma unroll

@@ -87,3 +87,51 @@ extern "C" int qpalm_b200_prof_report(char *buf, size_t buflen) {
   buf[buflen - 1] = 0;
   return 0;
 }
+
+// ---- latency micro-benchmarks (tools/microbench.py): SM clocks per dependent operation on one warp ----
+namespace {
+__global__ void k_lat(double *out, long long *clk, double x0) {
+  double x = x0 + threadIdx.x * 1e-9, y = 1.000000001;
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 256; i++) { x = fma(x, y, 1e-9); x = fma(x, y, 1e-9); x = fma(x, y, 1e-9); x = fma(x, y, 1e-9); }
+  long long t1 = clock64();
+  double s = x;
+#pragma unroll 1
+  for (int i = 0; i < 256; i++) { s = sqrt(s + 2.0); }
+  long long t2 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 256; i++) { s = 1.0 / (s + 2.0); }
+  long long t3 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 256; i++) { s = __shfl_sync(0xffffffffu, s, (i + 1) & 31) + 1.0; }
+  long long t4 = clock64();
+  double a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3, a4 = x + 4, a5 = x + 5, a6 = x + 6, a7 = x + 7;
+  long long t5 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 256; i++) {
+    a0 = fma(a0, y, 1e-9); a1 = fma(a1, y, 1e-9); a2 = fma(a2, y, 1e-9); a3 = fma(a3, y, 1e-9);
+    a4 = fma(a4, y, 1e-9); a5 = fma(a5, y, 1e-9); a6 = fma(a6, y, 1e-9); a7 = fma(a7, y, 1e-9);
+  }
+  long long t6 = clock64();
+  out[threadIdx.x + blockIdx.x * blockDim.x] = s + a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    clk[0] = (t1 - t0) / 1024; clk[1] = (t2 - t1) / 256; clk[2] = (t3 - t2) / 256; clk[3] = (t4 - t3) / 256; clk[4] = (t6 - t5);
+  }
+}
+}  // namespace
+
+// out[0] dependent DFMA latency, [1] sqrt (+add) latency, [2] reciprocal (+add), [3] shfl.f64 (+add), [4] clocks for
+// 256 x 8 independent DFMA per thread with `threads` threads per CTA on `ctas` CTAs (throughput probe)
+extern "C" int qpalm_b200_microbench(int ctas, int threads, long long *out5) {
+  double *d = nullptr; long long *c = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)ctas * threads));
+  QB_CUDA_TRY(cudaMalloc(&c, sizeof(long long) * 8));
+  k_lat<<<ctas, threads>>>(d, c, 1.0);
+  QB_CUDA_TRY(cudaDeviceSynchronize());
+  k_lat<<<ctas, threads>>>(d, c, 1.0);
+  QB_CUDA_TRY(cudaDeviceSynchronize());
+  QB_CUDA_TRY(cudaMemcpy(out5, c, sizeof(long long) * 5, cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(c);
+  return 0;
+}
