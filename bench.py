@@ -253,6 +253,41 @@ def hbm_roofline(lib, n, m):
 # ------------------------------------------------------------------------------------------------------
 # batched MPC workload (BASELINE config 4)
 # ------------------------------------------------------------------------------------------------------
+# dominant kernel per batch engine (share of the step from the ncu launch lists under profiles/): the persistent engine IS
+# one kernel; in the lock-step engine the single-CTA diagonal-block factorisation leads (39 %)
+DOMINANT_KERNEL = {"persistent": "kbp_solve", "lockstep": "k_diag_block"}
+
+
+def batch_algorithmic_bytes(n, m, stats):
+    """SURVEY.md 8(d) byte model (dense storage), summed over the steps the instances actually executed:
+    per inner iteration 2 B_A + B_Q + 8(38m + 26n) + 2 B_L (solve); per outer iteration 8(7m + 4n);
+    per refactorisation 8 |J| n + 2 B_L.  B_A = 8mn, B_Q = B_L = 8 n(n+1)/2."""
+    BA, BQ = 8.0 * m * n, 8.0 * n * (n + 1) / 2
+    BL = BQ
+    return (stats["inner"] * (2 * BA + BQ + 8.0 * (38 * m + 26 * n) + 2 * BL) + stats["outer"] * 8.0 * (7 * m + 4 * n)
+            + stats["refactorizations"] * 2 * BL + 8.0 * n * stats["refactor_J_sum"])
+
+
+def batch_roofline(n, m, nb, r, steps):
+    hbm, src = measured_peaks()
+    k = [v for name, v in r["kprof"].items() if r["dominant"] in name]
+    launches = sum(v["launches"] for v in k)
+    ms = sum(v["ms"] for v in k)
+    if not launches:
+        return None
+    per_launch_ms = ms / launches
+    if r["dominant"] == "kbp_solve":       # one launch = the whole sweep of nb instances
+        bytes_per_launch = batch_algorithmic_bytes(n, m, r["stats"])
+        note = "one launch solves the whole batch; bytes = SURVEY 8(d) model over the executed iterations (shared A, Q counted per instance)"
+    else:                                  # k_diag_block: read + write one 128 x 128 lower block, write its inverse, per instance
+        bytes_per_launch = nb * 3 * 8.0 * 128 * 129 / 2
+        note = "per launch: every instance's 128 x 128 diagonal block read + written, inverse written (upper bound: masked instances skip)"
+    ach = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": r["dominant"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "peak_source": src, "launches_timed": launches, "ms_per_launch": per_launch_ms, "share_of_step": ms / max(r["dev_ms"], 1e-9),
+            "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
+
+
 def bench_batch(args, steps, warmup, rank, world):
     import torch
     from qpalm_b200 import batch as qb
@@ -263,17 +298,28 @@ def bench_batch(args, steps, warmup, rank, world):
     h.upload(b.q, b.bmin, b.bmax)
     for _ in range(warmup):
         h.solve_resident(nb)
+    engine = h.stats(nb)["engine"]
+    dominant = DOMINANT_KERNEL[engine]
+    lib = h.lib
+    lib.qpalm_b200_prof_enable.argtypes = [C.c_char_p]
+    lib.qpalm_b200_prof_report.argtypes = [C.c_char_p, C.c_size_t]
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
+    lib.qpalm_b200_prof_enable(dominant.encode())     # CUDA-event pair around every launch of the dominant kernel only
     dev_ms = 0.0
     for _ in range(steps):
         dev_ms += h.solve_resident(nb)
     torch.cuda.synchronize()
+    buf = C.create_string_buffer(1 << 16)
+    lib.qpalm_b200_prof_report(buf, len(buf))
+    lib.qpalm_b200_prof_enable(b"")
+    kprof = json.loads(buf.value.decode() or "{}")
     clocks = sampler.stop()
     x, y, infos = h.download(nb)
+    stats = h.stats(nb)
     # e2e: host buffers in, host results out, every step
     if world > 1:
         torch.distributed.barrier()
@@ -283,7 +329,8 @@ def bench_batch(args, steps, warmup, rank, world):
     e2e_s = (time.perf_counter() - t0) / steps
     launches = h.last_launches() if hasattr(h, "last_launches") else None
     h.cleanup()
-    return dict(dev_ms=dev_ms, e2e_s=e2e_s, clocks=clocks, infos=infos, x=x, y=y, b=b, launches=launches,
+    return dict(dev_ms=dev_ms, e2e_s=e2e_s, clocks=clocks, infos=infos, x=x, y=y, b=b, launches=launches, stats=stats, kprof=kprof,
+                dominant=dominant,
                 h2d=8 * (b.q.size + b.bmin.size + b.bmax.size), d2h=8 * (x.size + y.size))
 
 
@@ -377,9 +424,11 @@ def main():
                      "e2e": {"value": total / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                      "clocks": r["clocks"], "gpu_launches": r["launches"]})
         if rank == 0:
-            hbm, src = measured_peaks()
             iters = float(np.mean([i["iter"] for i in r["infos"]]))
             line["config"]["mean_iterations"] = iters
+            line["config"]["engine"] = r["stats"]["engine"]
+            b0 = r["b"]
+            line["roofline"] = batch_roofline(b0.q.shape[1], b0.bmin.shape[1], args.batch, r, steps)
             if not args.no_cpu:
                 b = r["b"]
                 count = args.cpu_batch or min(args.batch, cpu_threads())

@@ -288,6 +288,9 @@ int  qpalm_b200_batch_solve(QPALMB200Batch *batch, c_int nb, const c_float *q, c
 int  qpalm_b200_batch_upload(QPALMB200Batch *batch, c_int nb, const c_float *q, const c_float *bmin, const c_float *bmax);
 int  qpalm_b200_batch_solve_resident(QPALMB200Batch *batch, c_int nb, double *device_ms);
 int  qpalm_b200_batch_download(QPALMB200Batch *batch, c_int nb, c_float *x, c_float *y, QPALMInfo *info);
+/* totals of the last solve over instances 0..nb-1: out5 = {inner iterations, outer iterations, refactorisations,
+ * sum of |J| over the refactorisations, engine (1 lock-step, 2 persistent)} -- inputs of the SURVEY 8(d) byte model */
+int  qpalm_b200_batch_stats(QPALMB200Batch *batch, c_int nb, double *out5);
 /* persistent engine, QPALM_B200_BATCH_PROF=1 at setup: per-instance SM-clock totals of 16 phases of the last solve */
 int  qpalm_b200_batch_phase_profile(QPALMB200Batch *batch, c_int nb, long long *out);
 long long qpalm_b200_batch_last_launches(const QPALMB200Batch *batch);   /* kernels launched by the last solve */

@@ -26,6 +26,8 @@ def _lib():
         lib.qpalm_b200_batch_download.restype = C.c_int
         lib.qpalm_b200_batch_last_launches.argtypes = [C.c_void_p]
         lib.qpalm_b200_batch_last_launches.restype = C.c_longlong
+        lib.qpalm_b200_batch_stats.argtypes = [C.c_void_p, abi.c_int, c_float_p]
+        lib.qpalm_b200_batch_stats.restype = C.c_int
         lib.qpalm_b200_batch_cleanup.argtypes = [C.c_void_p]
         lib.qpalm_b200_batch_cleanup.restype = None
         lib._batch_typed = True
@@ -87,6 +89,13 @@ class Batch:
         if rc:
             raise RuntimeError(f"batch_download failed: {rc}")
         return x, y, _infos(info, nb)
+
+    def stats(self, nb):
+        out = np.zeros(5)
+        if self.lib.qpalm_b200_batch_stats(self.h, nb, fptr(out)):
+            raise RuntimeError("batch_stats failed")
+        return dict(inner=out[0], outer=out[1], refactorizations=out[2], refactor_J_sum=out[3],
+                    engine={1: "lockstep", 2: "persistent"}.get(int(out[4]), "?"))
 
     def last_launches(self):
         return int(self.lib.qpalm_b200_batch_last_launches(self.h))

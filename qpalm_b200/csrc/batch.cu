@@ -287,6 +287,8 @@ __global__ void kb_control(int nb, int n, int m, BSet st, BCtl *ctl, const doubl
     else if (na) { if (ne + nl > 0) { mask_refac[b] = 1; mask_factor[b] = 1; c.scratch = !c.H_valid; } }
     else { mask_fq[b] = 1; mask_factor[b] = 1; }
     c.reset_newton = 0;
+    c.n_inner++;
+    if (mask_factor[b]) { c.n_refac++; c.refac_J += na; }
   }
   ctl[b] = c;
 }
@@ -1023,6 +1025,17 @@ extern "C" int qpalm_b200_batch_solve(QPALMB200Batch *B, c_int nb, const c_float
   if (int r = qpalm_b200_batch_solve_resident(B, nb, &ms)) return r;
   if (int r = qpalm_b200_batch_download(B, nb, x, y, info)) return r;
   if (info) for (c_int b = 0; b < nb; b++) info[b].solve_time = ms * 1e-3;
+  return 0;
+}
+
+// totals over the instances of the last download: [0] inner iterations, [1] outer iterations, [2] refactorisations,
+// [3] sum of |J| over them, [4] engine used (1 lock-step, 2 persistent)
+extern "C" int qpalm_b200_batch_stats(QPALMB200Batch *B, c_int nb, double *out5) {
+  if (!B || nb <= 0 || nb > B->nb_max) return 1;
+  QB_CUDA_TRY(cudaMemcpy(B->ctl_host.data(), B->ctl, sizeof(BCtl) * (size_t)nb, cudaMemcpyDeviceToHost));
+  double a = 0, o = 0, r = 0, j = 0;
+  for (c_int b = 0; b < nb; b++) { const BCtl &c = B->ctl_host[b]; a += c.n_inner; o += c.iter_out; r += c.n_refac; j += (double)c.refac_J; }
+  out5[0] = a; out5[1] = o; out5[2] = r; out5[3] = j; out5[4] = B->last_engine;
   return 0;
 }
 

@@ -13,6 +13,8 @@ struct BCtl {   // per-instance control state (device resident)
   int nb_enter, nb_leave, nb_active, H_valid, scratch, npos, nneg, boost;
   double gamma, gamma_prev, eps_abs_in, eps_rel_in, c, cinv, pri_res_norm, dua_res_norm, dua2_res_norm;
   double eps_pri, eps_dua, eps_dua_in, objective, beta;
+  int n_inner, n_refac;          // executed inner steps / Newton refactorisations (roofline byte model)
+  long long refac_J;             // sum of |J| over the refactorisations
 };
 
 struct BSet {   // settings the device needs (copied by value into kernels)

@@ -336,6 +336,8 @@ __device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
     else if (na) { if (ne + nl > 0) { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
     else { f.fq = 1; f.factor = 1; }
     c.reset_newton = 0;
+    c.n_inner++;
+    if (f.factor) { c.n_refac++; c.refac_J += na; }
   }
   P.ctl[b] = c;
 }
@@ -454,31 +456,34 @@ constexpr int SW = 16;
 // memory with ROLLED loops: a fully unrolled register version is ~3.4k straight-line instructions that one warp executes
 // once per call, i.e. it runs at instruction-fetch speed (measured 19 us per block vs ~3 us for this form).
 // Columns/rows >= w (ragged last panel) are skipped.  rd[c0 + j] = 1 / l_jj.
-__device__ __forceinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, int w, int *info) {
+__device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, int w, int *info) {
+  // one copy of the unrolled register kernel (noinline: both sub-panels and every panel share the same ~1k instructions,
+  // which therefore stay in the instruction cache; measured 3.1k clocks per block warm vs 9k for a rolled shared-memory form)
   const int lane = threadIdx.x & 31;
   const int row = c0 + lane;
-  const int wend = (w - c0 < SW) ? w - c0 : SW;   // live columns of this block
+  const int wend = (w - c0 < SW) ? w - c0 : SW;
   const bool live = lane < wend;
-  bool bad = false;
-#pragma unroll 1
-  for (int j = 0; j < wend; j++) {
-    const double pjj = Pn[(c0 + j) * LDP + c0 + j];
-    __syncwarp();   // every lane holds the pivot before lane j overwrites it
-    if (!(pjj > 0.0)) bad = true;
-    const double inv = rsqrt(pjj), ljj = pjj * inv;
-    double l = 0.0;
-    if (live && lane > j) { l = Pn[(c0 + j) * LDP + row] * inv; Pn[(c0 + j) * LDP + row] = l; }
-    else if (lane == j) { Pn[(c0 + j) * LDP + row] = ljj; rd[c0 + j] = inv; }
-    __syncwarp();
-    // rank-1 update of the remaining columns: the 15 column updates are independent, so the inner loop is unrolled with
-    // a run-time predicate (the outer loop stays rolled: compact code, see above)
+  double a[SW];
 #pragma unroll
-    for (int c = 1; c < SW; c++) {
-      if (c > j && c < wend && lane >= c && live)
-        Pn[(c0 + c) * LDP + row] = fma(-l, Pn[(c0 + j) * LDP + c0 + c], Pn[(c0 + c) * LDP + row]);
+  for (int c = 0; c < SW; c++) a[c] = (live && c < wend) ? ((c <= lane) ? Pn[(c0 + c) * LDP + row] : 0.0) : ((c == lane) ? 1.0 : 0.0);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < SW; j++) {
+    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(pjj > 0.0)) bad = true;
+    const double inv = rsqrt(pjj);
+    if (lane == j) { a[j] = pjj * inv; rd[c0 + j] = inv; }
+    else if (lane > j) a[j] *= inv;
+#pragma unroll
+    for (int c = 0; c < SW; c++) {
+      if (c > j) {   // constant bounds + predicate: see cta_potrf notes (a j-dependent bound leaves a[] in local memory)
+        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+        if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
+      }
     }
-    __syncwarp();
   }
+#pragma unroll
+  for (int c = 0; c < SW; c++) if (live && c <= lane && c < wend) Pn[(c0 + c) * LDP + row] = a[c];
   if (bad && lane == 0 && info) *info = 1;
 }
 

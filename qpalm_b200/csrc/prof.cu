@@ -135,3 +135,81 @@ extern "C" int qpalm_b200_microbench(int ctas, int threads, long long *out5) {
   cudaFree(d); cudaFree(c);
   return 0;
 }
+
+// ---- micro-benchmark of the 16 x 16 in-warp Cholesky variants (SM clocks per block) ----
+namespace {
+constexpr int MB_LDP = 241, MB_SW = 16;
+__device__ __forceinline__ void mb_diag_rolled(double *Pn, double *rd, int c0, int w) {
+  const int lane = threadIdx.x & 31, row = c0 + lane;
+  const int wend = (w - c0 < MB_SW) ? w - c0 : MB_SW;
+  const bool live = lane < wend;
+#pragma unroll 1
+  for (int j = 0; j < wend; j++) {
+    const double pjj = Pn[(c0 + j) * MB_LDP + c0 + j];
+    __syncwarp();
+    const double inv = rsqrt(pjj), ljj = pjj * inv;
+    double l = 0.0;
+    if (live && lane > j) { l = Pn[(c0 + j) * MB_LDP + row] * inv; Pn[(c0 + j) * MB_LDP + row] = l; }
+    else if (lane == j) { Pn[(c0 + j) * MB_LDP + row] = ljj; rd[c0 + j] = inv; }
+    __syncwarp();
+    double tv[MB_SW], mv[MB_SW];
+#pragma unroll
+    for (int c = 1; c < MB_SW; c++) {
+      const bool on = c > j && c < wend && lane >= c && live;
+      tv[c] = on ? Pn[(c0 + c) * MB_LDP + row] : 0.0;
+      mv[c] = on ? Pn[(c0 + j) * MB_LDP + c0 + c] : 0.0;
+    }
+#pragma unroll
+    for (int c = 1; c < MB_SW; c++)
+      if (c > j && c < wend && lane >= c && live) Pn[(c0 + c) * MB_LDP + row] = fma(-l, mv[c], tv[c]);
+    __syncwarp();
+  }
+}
+// column-oriented variant: lane = column c; each lane keeps its column's pending diagonal/sub-diagonal updates in
+// registers?  (not possible without static indexing) -- instead: row-per-lane registers, j loop unrolled
+__device__ __forceinline__ void mb_diag_regs(double *Pn, double *rd, int c0) {
+  const int lane = threadIdx.x & 31, row = c0 + lane;
+  double a[MB_SW];
+#pragma unroll
+  for (int c = 0; c < MB_SW; c++) a[c] = (lane < MB_SW) ? ((c <= lane) ? Pn[(c0 + c) * MB_LDP + row] : 0.0) : ((c == lane) ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < MB_SW; j++) {
+    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+    const double inv = rsqrt(pjj);
+    if (lane == j) { a[j] = pjj * inv; rd[c0 + j] = inv; }
+    else if (lane > j) a[j] *= inv;
+#pragma unroll
+    for (int c = 0; c < MB_SW; c++)
+      if (c > j) { const double lcj = __shfl_sync(0xffffffffu, a[j], c); if (lane >= c) a[c] = fma(-a[j], lcj, a[c]); }
+  }
+#pragma unroll
+  for (int c = 0; c < MB_SW; c++) if (lane < MB_SW && c <= lane) Pn[(c0 + c) * MB_LDP + row] = a[c];
+}
+__global__ void k_mb_diag(long long *clk, double *sink, int reps) {
+  __shared__ double Pn[16 * MB_LDP];
+  __shared__ double rd[64];
+  const int lane = threadIdx.x;
+  for (int v = 0; v < 2; v++) {
+    long long total = 0;
+    for (int r = 0; r < reps; r++) {
+      for (int c = 0; c < 16; c++) Pn[c * MB_LDP + lane] = (c == lane) ? 40.0 + lane : 1.0 / (1 + c + lane);
+      __syncwarp();
+      const long long t0 = clock64();
+      if (v == 0) mb_diag_rolled(Pn, rd, 0, 16); else mb_diag_regs(Pn, rd, 0);
+      __syncwarp();
+      total += clock64() - t0;
+    }
+    if (lane == 0) clk[v] = total / reps;
+    sink[lane + 32 * v] = Pn[(lane & 15) * MB_LDP + lane] + rd[lane & 15];
+  }
+}
+}  // namespace
+extern "C" int qpalm_b200_microbench_diag(long long *out2) {
+  long long *c = nullptr; double *d = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&c, 64)); QB_CUDA_TRY(cudaMalloc(&d, 8 * 64));
+  k_mb_diag<<<1, 32>>>(c, d, 20);
+  QB_CUDA_TRY(cudaDeviceSynchronize());
+  QB_CUDA_TRY(cudaMemcpy(out2, c, 16, cudaMemcpyDeviceToHost));
+  cudaFree(c); cudaFree(d);
+  return 0;
+}
