@@ -437,13 +437,22 @@ def main():
                                         "sample": f"first {count} instances of rank 0's batch, one single-threaded reference process per core"}
                 line["config"]["cpu_mean_iterations"] = float(np.mean(cpu_iters))
     else:
+        if world > 1:   # BASELINE config 3 on N GPUs: ONE QP, constraint rows sharded over the ranks (csrc/shard.cu, NCCL)
+            from qpalm_b200 import rowshard
+            rowshard.init(rank, world, torch.device("cuda", local))
+            line["scaling"] = "strong"
         dense, p = bench_dense(args, lib, steps, warmup)
+        t = torch.tensor([dense["ms_per_solve"], dense["e2e_s"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dense["ms_per_solve"], dense["e2e_s"] = float(t[0]), float(t[1])
         dev_ms = dense["ms_per_solve"]
-        line.update({"metric": "qp_solves_per_sec", "unit": "solves/s", "value": world * 1e3 / dev_ms, "ms_per_step": dev_ms,
-                     "config": {"workload": f"dense random convex QP n={args.n} m={args.m} eps 1e-6 (replica per GPU)",
+        line.update({"metric": "qp_solves_per_sec", "unit": "solves/s", "value": 1e3 / dev_ms, "ms_per_step": dev_ms,
+                     "config": {"workload": f"dense random convex QP n={args.n} m={args.m} eps 1e-6"
+                                            + (f" (constraint rows sharded over {world} GPUs, NCCL)" if world > 1 else ""),
                                 "l2": "inputs larger than L2 (A' is %.2f GB)" % (8.0 * args.n * args.m / 1e9),
                                 "status": dense["status"], "iter": dense["iter"], "iter_out": dense["iter_out"]},
-                     "e2e": {"value": world / dense["e2e_s"], "unit": "solves/s", "h2d_bytes_per_step": dense["h2d"], "d2h_bytes_per_step": dense["d2h"]},
+                     "e2e": {"value": 1.0 / dense["e2e_s"], "unit": "solves/s", "h2d_bytes_per_step": dense["h2d"], "d2h_bytes_per_step": dense["d2h"]},
                      "clocks": dense["clocks"], "gpu_launches": dense["launches"] // steps})
         if rank == 0:
             line["roofline"] = tensor_roofline(lib, args.n, dense["refactor_active_avg"], dense)

@@ -274,6 +274,17 @@ int qpalm_b200_bench_dmma_peak(double *tflops_out);
 int qpalm_b200_bench_gemv(c_int n, c_int m, c_int reps, double *ms_cols_out, double *ms_rows_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Part 2b -- row-sharding of one large dense QP over the GPUs of a box (additive; SURVEY.md 8(e), BASELINE config 3).
+ * One process per GPU.  Rank 0 makes a 128-byte NCCL id (shard_unique_id), the caller distributes it, every rank calls
+ * shard_init and then the ordinary qpalm_setup / qpalm_solve with the SAME full problem data: the library keeps only its
+ * block of constraint rows of A on the device and exchanges A d (allgather), A' yh and the Schur-complement SYRK partials
+ * (allreduce) over NCCL.  Every rank returns the same full solution.  Sparse A: replicas only (no sharding).
+ * ---------------------------------------------------------------------------------------------- */
+int  qpalm_b200_shard_unique_id(char *out128);
+int  qpalm_b200_shard_init(int rank, int world, const char *id128);
+void qpalm_b200_shard_finalize(void);
+
+/* ------------------------------------------------------------------------------------------------
  * Part 3 -- batch entry point (additive).  `nb` QPs sharing Q, A (values and pattern) and settings
  * but with their own q, bmin, bmax.  Each instance's result equals what qpalm_setup + qpalm_solve
  * return for that instance alone.  q: nb x n, bmin/bmax: nb x m (row-major, one instance per row).

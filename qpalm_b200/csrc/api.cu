@@ -383,6 +383,7 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 // only when it is predicted to be cheaper than the last measured refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0 || k > e->updown_max_rank) return false;
+  if (e->sh_world > 1) return false;   // row-sharded: the entering rows live on different ranks; refactorise (allreduced H)
   if (e->updown_force) return true;
   const double t_ud = (e->npad / 32.0) * (0.030 + 0.012 * k);
   const double t_rf = e->last_refactor_ms > 0 ? e->last_refactor_ms : 1e-9 * ((double)e->n * e->n * e->n / 3.0) / 8.0 + 0.2;

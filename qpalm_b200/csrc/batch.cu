@@ -820,6 +820,10 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
     fprintf(stderr, "[qpalm_b200] batch: 2m = %d exceeds the in-CTA line-search sort capacity (%d)\n", 2 * m, kSortMax);
     return nullptr;
   }
+  if (shard_world() > 1) {
+    fprintf(stderr, "[qpalm_b200] batch: instances shard by index across ranks (qpalm_b200/shard.py); do not combine with row-sharding\n");
+    return nullptr;
+  }
   QPALMB200Batch *B = new QPALMB200Batch();
   B->nb_max = nb_max; B->n = n; B->m = m; B->m2 = 2 * m;
   std::vector<double> zn((size_t)n + 1, 0.0), zm((size_t)m + 1, 0.0);

@@ -52,6 +52,9 @@ struct Engine {
   cudaStream_t stream = nullptr;
   int n = 0, m = 0, npad = 0, ld = 0;
   bool A_dense = false, Q_dense = false;
+  // row-sharding (shard.cu): this rank holds constraint rows [m_lo, m_lo + m_loc) of A in `At` (n x m_loc); vectors of
+  // length m are replicated and padded to sh_world * m_cap entries so that the in-place allgather blocks are equal-sized
+  int sh_world = 1, sh_rank = 0, m_lo = 0, m_loc = 0, m_cap = 0;
   SparseDev A_csr, A_csc, Q_csr;      // sparse forms
   double *At = nullptr;               // dense A' (n x m, ld n)
   double *Qd = nullptr;               // dense Q  (n x n, ld n), full symmetric
@@ -126,6 +129,12 @@ int upload(Engine *e, double *dst, const double *src, int len);
 int download(Engine *e, double *dst, const double *src, int len);
 int download_int(Engine *e, long long *dst, const int *src, int len);   // widens to int64
 int sync_scalars(Engine *e);   // scal_dev -> scal_host, stream synchronize
+
+// ---- row-sharding collectives (shard.cu; no-ops on a single GPU) ------------------------------------
+int shard_world();
+int shard_rank();
+int shard_allreduce(const double *send, double *recv, size_t count, bool max_op, cudaStream_t s);
+int shard_allgather(double *buf, size_t count_per_rank, cudaStream_t s);
 
 // ---- iteration steps (each: a handful of fused kernels, no host sync) ------------------------------
 int step_residuals(Engine *e, bool proximal, double gamma, double tau);  // a3 + a4 + a5 counts + a14 reductions

@@ -208,14 +208,21 @@ static int gemv_rows(Engine *e, int nrows, int ncols, int ld, const double *M, c
 int spmv_A(Engine *e, const double *x, double *y) {
   if (e->m == 0) return 0;
   e->n_spmv++;
-  if (e->A_dense) QB_LAUNCH(k_gemv_cols, cdiv(e->m, 8), 256, 0, e->stream, e->n, e->m, e->n, e->At, x, y);
-  else QB_LAUNCH(k_csr_spmv, cdiv(e->m, 8), 256, 0, e->stream, e->m, e->A_csr.p, e->A_csr.i, e->A_csr.x, x, y);
+  if (e->A_dense) {
+    if (e->m_loc > 0) QB_LAUNCH(k_gemv_cols, cdiv(e->m_loc, 8), 256, 0, e->stream, e->n, e->m_loc, e->n, e->At, x, y + e->m_lo);
+    if (e->sh_world > 1) return shard_allgather(y, (size_t)e->m_cap, e->stream);   // every rank ends with the full A x
+  } else QB_LAUNCH(k_csr_spmv, cdiv(e->m, 8), 256, 0, e->stream, e->m, e->A_csr.p, e->A_csr.i, e->A_csr.x, x, y);
   return 0;
 }
 int spmv_At(Engine *e, const double *x, double *y) {
   e->n_spmv++;
   if (e->m == 0) return vec_set(e, y, 0.0, e->n);
-  if (e->A_dense) return gemv_rows(e, e->n, e->m, e->n, e->At, x, y);
+  if (e->A_dense) {
+    if (e->m_loc > 0) { if (int r = gemv_rows(e, e->n, e->m_loc, e->n, e->At, x + e->m_lo, y)) return r; }
+    else if (int r = vec_set(e, y, 0.0, e->n)) return r;
+    if (e->sh_world > 1) return shard_allreduce(y, y, (size_t)e->n, false, e->stream);   // sum of the per-rank partials
+    return 0;
+  }
   QB_LAUNCH(k_csr_spmv, cdiv(e->n, 8), 256, 0, e->stream, e->n, e->A_csc.p, e->A_csc.i, e->A_csc.x, x, y);
   return 0;
 }
@@ -416,14 +423,14 @@ int step_commit_active(Engine *e) { return ivec_copy(e, e->active, e->active_old
 // -- the columns cholmod_submatrix extracts from At_sqrt_sigma (solver_interface.c:417,435,493)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gather_dense(int n, int npad, const double *__restrict__ At, const int *__restrict__ list,
-                               const double *__restrict__ scale, int scale_by_row, int cnt, double *W, int ldw) {
+                               const double *__restrict__ scale, int scale_by_row, int cnt, double *W, int ldw, int m_lo, int m_loc) {
   const int c = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npad) return;
   double v = 0.0;
   if (c < cnt && i < n) {
-    const int row = list[c];
-    v = At[(size_t)i + (size_t)n * row] * (scale_by_row ? scale[row] : scale[c]);
+    const int row = list[c], loc = row - m_lo;   // rows owned by another rank contribute a zero column here
+    if (loc >= 0 && loc < m_loc) v = At[(size_t)i + (size_t)n * loc] * (scale_by_row ? scale[row] : scale[c]);
   }
   W[(size_t)i + (size_t)ldw * c] = v;
 }
@@ -443,7 +450,7 @@ __global__ void k_gather_csr(int npad, const int *__restrict__ p, const int *__r
 static int gather_rows(Engine *e, const int *list, const double *scale, bool scale_by_row, int cnt, int kpad) {
   if (e->A_dense) {
     dim3 grid(cdiv(e->npad, 256), kpad);
-    QB_LAUNCH(k_gather_dense, grid, 256, 0, e->stream, e->n, e->npad, e->At, list, scale, scale_by_row ? 1 : 0, cnt, e->W, e->ld);
+    QB_LAUNCH(k_gather_dense, grid, 256, 0, e->stream, e->n, e->npad, e->At, list, scale, scale_by_row ? 1 : 0, cnt, e->W, e->ld, e->m_lo, e->m_loc);
   } else {
     QB_LAUNCH(k_gather_csr, kpad, 256, 0, e->stream, e->npad, e->A_csr.p, e->A_csr.i, e->A_csr.x, list, scale,
               scale_by_row ? 1 : 0, cnt, e->W, e->ld);
@@ -477,7 +484,12 @@ __global__ void k_add_diag_pad(int n, int npad, double *L, int ld, double beta) 
   double *p = L + (size_t)i * (ld + 1);
   *p = (i < n) ? (*p + beta) : 1.0;
 }
-static int init_lower_from_Q(Engine *e, double *dst) {
+// partial: dst is this rank's term of a sum over ranks (the H record of a row-sharded problem) -- Q enters on rank 0 only
+static int init_lower_from_Q(Engine *e, double *dst, bool partial = false) {
+  if (partial && e->sh_world > 1 && e->sh_rank != 0) {
+    QB_CUDA_TRY(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)e->ld * e->npad, e->stream));
+    return 0;
+  }
   if (e->Q_dense) {
     dim3 grid(cdiv(e->npad, 256), e->npad);
     QB_LAUNCH(k_init_lower_from_dense, grid, 256, 0, e->stream, e->n, e->npad, e->Qd, dst, e->ld);
@@ -521,13 +533,16 @@ int step_newton_refactor(Engine *e, bool with_constraints, bool from_scratch, do
         from_scratch = true;
         continue;
       }
-      if (from_scratch) { if (int r = init_lower_from_Q(e, e->H)) return r; }
+      if (from_scratch) { if (int r = init_lower_from_Q(e, e->H, true)) return r; }
       if (int r = syrk_list(e, e->H, e->list_pos, e->w_pos, false, npos, 1.0)) return r;
       if (int r = syrk_list(e, e->H, e->list_neg, e->w_neg, false, nneg, -1.0)) return r;
       break;
     }
     e->H_valid = true;
-    if (int r = copy_lower_add_diag(e->stream, e->n, e->npad, e->H, e->L, e->ld, beta)) return r;
+    if (e->sh_world > 1) {   // L <- sum over ranks of the H partials, then + beta I (and the identity pad)
+      if (int r = shard_allreduce(e->H, e->L, (size_t)e->ld * e->npad, false, e->stream)) return r;
+      QB_LAUNCH(k_add_diag_pad, cdiv(e->npad, 256), 256, 0, e->stream, e->n, e->npad, e->L, e->ld, beta);
+    } else if (int r = copy_lower_add_diag(e->stream, e->n, e->npad, e->H, e->L, e->ld, beta)) return r;
   }
   if (int r = potrf_lower(e->stream, e->npad, e->L, e->ld, e->invdiag, e->info_dev)) return r;
   QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
@@ -946,6 +961,7 @@ int step_gershgorin_AtSA(Engine *e, double *ub_host) {
   if (int r = sync_scalars(e)) return r;
   const int npos = (int)e->scal_host[S_TMP0];
   if (int r = syrk_list(e, e->L, e->list_pos, e->w_pos, false, npos, 1.0)) return r;
+  if (e->sh_world > 1) { if (int r = shard_allreduce(e->L, e->L, (size_t)e->ld * e->npad, false, e->stream)) return r; }
   if (int r = sym_abs_rowsums(e->stream, e->n, e->L, e->ld, e->tmp_n)) return r;
   const int g = red_grid(e->n);
   QB_LAUNCH(k_max_reduce, g, kRedThreads, 0, e->stream, e->n, e->tmp_n, e->partials, S_TMP4);
@@ -1096,12 +1112,19 @@ int ruiz_norms_public(Engine *e, double *Dt, double *Et) {
   const int n = e->n, m = e->m;
   if (m == 0) return vec_set(e, Dt, 0.0, n);
   if (e->A_dense) {
-    int splits = e->gemv_splits; if (splits > m) splits = m;
-    const int cps = cdiv(m, splits); splits = cdiv(m, cps);
-    dim3 grid(cdiv(n, 128), splits);
-    QB_LAUNCH(k_dense_absmax_rows, grid, 128, 0, e->stream, n, m, n, e->At, e->gemv_partials, cps);
-    QB_LAUNCH(k_max_splits, cdiv(n, 256), 256, 0, e->stream, n, splits, e->gemv_partials, Dt);
-    QB_LAUNCH(k_dense_absmax_cols, cdiv(m, 8), 256, 0, e->stream, n, m, n, e->At, Et);
+    const int ml = e->m_loc;   // this rank's rows (all of them on a single GPU)
+    if (ml > 0) {
+      int splits = e->gemv_splits; if (splits > ml) splits = ml;
+      const int cps = cdiv(ml, splits); splits = cdiv(ml, cps);
+      dim3 grid(cdiv(n, 128), splits);
+      QB_LAUNCH(k_dense_absmax_rows, grid, 128, 0, e->stream, n, ml, n, e->At, e->gemv_partials, cps);
+      QB_LAUNCH(k_max_splits, cdiv(n, 256), 256, 0, e->stream, n, splits, e->gemv_partials, Dt);
+      QB_LAUNCH(k_dense_absmax_cols, cdiv(ml, 8), 256, 0, e->stream, n, ml, n, e->At, Et + e->m_lo);
+    } else if (int r = vec_set(e, Dt, 0.0, n)) return r;
+    if (e->sh_world > 1) {   // column norms: max over the ranks' row blocks; row norms: gather the blocks
+      if (int r = shard_allreduce(Dt, Dt, (size_t)n, true, e->stream)) return r;
+      if (int r = shard_allgather(Et, (size_t)e->m_cap, e->stream)) return r;
+    }
   } else {
     QB_LAUNCH(k_csr_absmax, cdiv(n, 8), 256, 0, e->stream, n, e->A_csc.p, e->A_csc.x, Dt);
     QB_LAUNCH(k_csr_absmax, cdiv(m, 8), 256, 0, e->stream, m, e->A_csr.p, e->A_csr.x, Et);
@@ -1129,8 +1152,10 @@ static int ruiz_impl(Engine *e, int iters, bool use_Qx, double *c_out) {
     QB_LAUNCH(k_ruiz_post, cdiv(n, 256), 256, 0, e->stream, n, Dt, e->D);
     QB_LAUNCH(k_ruiz_post, cdiv(m, 256), 256, 0, e->stream, m, Et, e->E);
     if (e->A_dense) {
-      dim3 grid(cdiv(n, 256), m);
-      QB_LAUNCH(k_scale_dense_At, grid, 256, 0, e->stream, n, m, e->At, Et, Dt);
+      if (e->m_loc > 0) {
+        dim3 grid(cdiv(n, 256), e->m_loc);
+        QB_LAUNCH(k_scale_dense_At, grid, 256, 0, e->stream, n, e->m_loc, e->At, Et + e->m_lo, Dt);
+      }
     } else {
       QB_LAUNCH(k_scale_sparse, cdiv(n, 8), 256, 0, e->stream, n, e->A_csc.p, e->A_csc.i, e->A_csc.x, Et, Dt, 0);
       QB_LAUNCH(k_scale_sparse, cdiv(m, 8), 256, 0, e->stream, m, e->A_csr.p, e->A_csr.i, e->A_csr.x, Et, Dt, 1);
@@ -1369,20 +1394,33 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   const long long nnzA = m > 0 ? Ap[n] : 0;
   // ---- A ----
   e->A_dense = (m > 0) && ((double)nnzA >= 0.25 * (double)m * (double)n);
+  e->m_lo = 0; e->m_loc = m; e->m_cap = m;
+  if (e->A_dense && shard_world() > 1 && m >= shard_world()) {   // row-sharded dense QP (shard.cu): keep only this rank's rows of A
+    e->sh_world = shard_world(); e->sh_rank = shard_rank();
+    e->m_cap = cdiv(m, e->sh_world);
+    e->m_lo = e->sh_rank * e->m_cap;
+    e->m_loc = m - e->m_lo < e->m_cap ? m - e->m_lo : e->m_cap;
+    if (e->m_loc < 0) e->m_loc = 0;
+  }
   if (m > 0 && e->A_dense) {
+    const int ml = e->m_loc, lo = e->m_lo;
     double *tmp = nullptr;
-    if (int r = dev_alloc((void **)&tmp, sizeof(double) * (size_t)m * n)) return r;
-    if (nnzA == (long long)m * n) {
-      QB_CUDA_TRY(cudaMemcpy(tmp, Ax, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice));
-    } else {
-      double *hd = (double *)calloc((size_t)m * n, sizeof(double));
-      for (int j = 0; j < n; j++) for (long long k = Ap[j]; k < Ap[j + 1]; k++) hd[(size_t)Ai[k] + (size_t)m * j] = Ax[k];
-      QB_CUDA_TRY(cudaMemcpy(tmp, hd, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice));
+    if (int r = dev_alloc((void **)&tmp, sizeof(double) * (size_t)(ml ? ml : 1) * n)) return r;
+    if (ml > 0 && nnzA == (long long)m * n) {   // complete dense CSC: rows lo..lo+ml-1 of every column
+      QB_CUDA_TRY(cudaMemcpy2D(tmp, sizeof(double) * (size_t)ml, Ax + lo, sizeof(double) * (size_t)m, sizeof(double) * (size_t)ml,
+                               (size_t)n, cudaMemcpyHostToDevice));
+    } else if (ml > 0) {
+      double *hd = (double *)calloc((size_t)ml * n, sizeof(double));
+      for (int j = 0; j < n; j++)
+        for (long long k = Ap[j]; k < Ap[j + 1]; k++) { const long long r = Ai[k] - lo; if (r >= 0 && r < ml) hd[(size_t)r + (size_t)ml * j] = Ax[k]; }
+      QB_CUDA_TRY(cudaMemcpy(tmp, hd, sizeof(double) * (size_t)ml * n, cudaMemcpyHostToDevice));
       free(hd);
     }
-    if (int r = dev_alloc((void **)&e->At, sizeof(double) * (size_t)m * n)) return r;
-    dim3 grid(cdiv(m, 32), cdiv(n, 32)), block(32, 8);
-    QB_LAUNCH(k_transpose_to_At, grid, block, 0, e->stream, m, n, tmp, e->At);
+    if (int r = dev_alloc((void **)&e->At, sizeof(double) * (size_t)(ml ? ml : 1) * n)) return r;
+    if (ml > 0) {
+      dim3 grid(cdiv(ml, 32), cdiv(n, 32)), block(32, 8);
+      QB_LAUNCH(k_transpose_to_At, grid, block, 0, e->stream, ml, n, tmp, e->At);
+    }
     QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
     cudaFree(tmp);
   } else if (m > 0) {
@@ -1436,11 +1474,12 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     free(cnt); free(start); free(fill); free(rj); free(rx);
   }
   // ---- vectors ----
-  const size_t N = (size_t)n, M = (size_t)m;
+  const size_t N = (size_t)n, M = (size_t)(e->sh_world > 1 ? e->sh_world * e->m_cap : m);   // m-vectors padded for the in-place allgather
   auto dv = [&](double **p, size_t len) { return dev_alloc((void **)p, sizeof(double) * (len ? len : 1)); };
   auto iv = [&](int **p, size_t len) { return dev_alloc((void **)p, sizeof(int) * (len ? len : 1)); };
   int rc = 0;
-  rc |= up(&e->q, q, N); rc |= up(&e->bmin, bmin, M); rc |= up(&e->bmax, bmax, M);
+  rc |= up(&e->q, q, N); rc |= dv(&e->bmin, M); rc |= dv(&e->bmax, M);
+  if (!rc && m > 0) { rc |= upload(e, e->bmin, bmin, m); rc |= upload(e, e->bmax, bmax, m); }
   rc |= dv(&e->D, N); rc |= dv(&e->Dinv, N); rc |= dv(&e->E, M); rc |= dv(&e->Einv, M);
   rc |= dv(&e->x, N); rc |= dv(&e->y, M); rc |= dv(&e->Ax, M); rc |= dv(&e->Qx, N); rc |= dv(&e->Aty, N);
   rc |= dv(&e->x_prev, N); rc |= dv(&e->x0, N);

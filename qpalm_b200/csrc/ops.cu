@@ -353,7 +353,7 @@ extern "C" int qpalm_b200_bench_gemv(c_int n_, c_int m_, c_int reps, double *ms_
   const int n = (int)n_, m = (int)m_;
   Engine e;   // minimal engine: only what the two dense kernels need
   QB_CUDA_TRY(cudaStreamCreate(&e.stream));
-  e.n = n; e.m = m; e.A_dense = true;
+  e.n = n; e.m = m; e.A_dense = true; e.m_loc = m; e.m_cap = m;
   QB_CUDA_TRY(cudaMalloc(&e.At, sizeof(double) * (size_t)n * m));
   QB_CUDA_TRY(cudaMalloc(&e.x, sizeof(double) * n)); QB_CUDA_TRY(cudaMalloc(&e.y, sizeof(double) * m));
   QB_CUDA_TRY(cudaMalloc(&e.Ax, sizeof(double) * m)); QB_CUDA_TRY(cudaMalloc(&e.Aty, sizeof(double) * n));
