@@ -256,6 +256,9 @@ def hbm_roofline(lib, n, m):
 # dominant kernel per batch engine (share of the step from the ncu launch lists under profiles/): the persistent engine IS
 # one kernel; in the lock-step engine the single-CTA diagonal-block factorisation leads (39 %)
 DOMINANT_KERNEL = {"persistent": "kbp_solve", "lockstep": "k_diag_block"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the `ncu --set full` capture of this command at the default
+# --batch 512 (profiles/r01b_ncu_full_kbp_solve.txt: 35.09 GB read + 38.77 GB written)
+NCU_TRAFFIC_BYTES = {("kbp_solve", 512): 35.088253e9 + 38.774333e9}
 
 
 def batch_algorithmic_bytes(n, m, stats):
@@ -283,7 +286,8 @@ def batch_roofline(n, m, nb, r, steps):
         bytes_per_launch = nb * 3 * 8.0 * 128 * 129 / 2
         note = "per launch: every instance's 128 x 128 diagonal block read + written, inverse written (upper bound: masked instances skip)"
     ach = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": r["dominant"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+    return {"bound": "hbm", "kernel": r["dominant"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "traffic": NCU_TRAFFIC_BYTES.get((r["dominant"], nb)), "traffic_source": "profiles/r01b_ncu_full_kbp_solve.txt",
             "peak_source": src, "launches_timed": launches, "ms_per_launch": per_launch_ms, "share_of_step": ms / max(r["dev_ms"], 1e-9),
             "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
 

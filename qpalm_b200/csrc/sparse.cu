@@ -1,0 +1,676 @@
+// sparse.cu -- device side of the supernodal multifrontal Cholesky (see sparse.cuh for the design).
+//
+// Factor layout: supernode s owns permuted columns [first, first + ns) and the sorted rows R_s (nr of them) below;
+// its panel is column-major (nf = ns + nr) x ns with leading dimension nf; its update block U_s is nr x nr (ld nr),
+// lower triangle used.  "Front" index space of s: 0..ns-1 = own columns, ns..nf-1 = R_s.
+//
+// Numeric factorization, level l (all supernodes whose children are done):
+//   k_mf_extend   U_s <- 0, then panel_s / U_s += U_c scattered through rel_c for every child c (fixed order; each
+//                 CTA owns a range of target columns => no atomics, bit-reproducible)
+//   per 32-column block kb of the panel:   k_mf_diag (32 x 32 Cholesky in registers, one warp per front),
+//                 k_mf_trsm (rows below the block, one thread per row), k_mf_syrk (trailing update of the rest of the
+//                 panel and of U_s, 64 x 64 tiles, 4 x 4 per thread)
+//   levels whose fronts all fit in shared memory take k_mf_small instead: ONE launch does extend-add + partial
+//   factorization + write-back with the whole front resident in shared memory.
+// Solves: k_mf_fwd / k_mf_bwd, one CTA per supernode per level, per-supernode update vectors (pull-based).
+// Rank-k update/downdate: k_ud_mark marks the etree paths, k_ud_sweep walks them (one CTA, columns in ascending order).
+#include "sparse.cuh"
+#include "sparse_host.h"
+
+#include <string.h>
+#include <vector>
+
+namespace qb {
+
+struct SpDev {
+  int n, nsuper;
+  const int *perm, *iperm, *sn_of_col, *first, *rows_off, *rowidx, *rel, *sn_parent, *child_ptr, *child_idx, *lvl_sn;
+  const long long *panel_off, *upd_off;
+};
+
+struct SparseChol {
+  SymHost h;
+  SparseCholInfo info;
+  SpDev d;
+  std::vector<void *> allocs;
+  double *upd = nullptr;      // update blocks (sum nr^2)
+  double *uvec = nullptr;     // per-supernode update vectors of the solves (sum nr)
+  double *v = nullptr;        // permuted rhs / solution (n)
+  double *W = nullptr;        // rank-k panel, n x 8 permuted
+  int *mark = nullptr;        // nsuper
+  int small_nf = 0;           // fronts up to this size use the shared-memory kernel
+  int small_smem_max = 0;
+};
+
+template <typename T>
+static int up_vec(SparseChol *sc, const T **dst, const std::vector<T> &src) {
+  void *p = nullptr;
+  const size_t bytes = sizeof(T) * (src.size() ? src.size() : 1);
+  QB_CUDA_TRY(cudaMalloc(&p, bytes));
+  if (!src.empty()) QB_CUDA_TRY(cudaMemcpy(p, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+  sc->allocs.push_back(p);
+  *dst = (const T *)p;
+  return 0;
+}
+template <typename T>
+static int dev_buf(SparseChol *sc, T **dst, size_t count) {
+  void *p = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+  QB_CUDA_TRY(cudaMemset(p, 0, sizeof(T) * (count ? count : 1)));
+  sc->allocs.push_back(p);
+  *dst = (T *)p;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-front kernel configuration
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallMaxNf = 160;   // (160 * 161 / 2 + pad) * 8 B of shared memory < 227 KB
+__host__ __device__ inline int tri_ld(int nf) { return nf | 1; }   // odd leading dimension: conflict-free column walks
+
+int sparse_chol_analyze(SparseChol **out, int n, int m, const int *Acsc_p, const int *Acsc_i, const int *Acsr_p,
+                        const int *Acsr_j, const long long *Qp, const long long *Qi, bool force, cudaStream_t stream) {
+  *out = nullptr;
+  SparseChol *sc = new SparseChol();
+  const int r = symbolic_analyze(n, m, Acsc_p, Acsc_i, Acsr_p, Acsr_j, Qp, Qi, force, &sc->h);
+  if (r == 1) { delete sc; return 0; }
+  if (r != 0) { delete sc; return 3; }
+  SymHost &h = sc->h;
+  // the sparse path pays off only when the factor is much smaller than the dense triangle
+  const double dense_tri = 0.5 * (double)n * ((double)n + 1.0);
+  if (!force && ((double)h.nnzL > 0.30 * dense_tri || n < 512)) { delete sc; return 0; }
+  size_t free_b = 0, total_b = 0;
+  QB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const double need = 8.0 * ((double)h.nnzL * 2 + (double)h.upd_total) + (1u << 28);
+  if (need > (double)free_b) {
+    fprintf(stderr, "[qpalm_b200] sparse Newton path needs %.1f GB (factor %.1f GB, update blocks %.1f GB) but only %.1f GB "
+                    "of HBM is free\n", need / 1e9, 8.0 * h.nnzL / 1e9, 8.0 * h.upd_total / 1e9, free_b / 1e9);
+    delete sc; return 2;
+  }
+  SparseCholInfo &I = sc->info;
+  I.n = n; I.nsuper = h.nsuper; I.nlevels = h.nlevels; I.max_ns = h.max_ns; I.max_nf = h.max_nf;
+  I.nnzL = h.nnzL; I.upd_entries = h.upd_total; I.nnzS = h.nnzS; I.flops = h.flops;
+  SpDev &d = sc->d;
+  d.n = n; d.nsuper = h.nsuper;
+  int rc = 0;
+  rc |= up_vec(sc, &d.perm, h.perm); rc |= up_vec(sc, &d.iperm, h.iperm); rc |= up_vec(sc, &d.sn_of_col, h.sn_of_col);
+  rc |= up_vec(sc, &d.first, h.sn_first); rc |= up_vec(sc, &d.rows_off, h.rows_off); rc |= up_vec(sc, &d.rowidx, h.rowidx);
+  rc |= up_vec(sc, &d.rel, h.rel); rc |= up_vec(sc, &d.sn_parent, h.sn_parent); rc |= up_vec(sc, &d.child_ptr, h.child_ptr);
+  rc |= up_vec(sc, &d.child_idx, h.child_idx); rc |= up_vec(sc, &d.lvl_sn, h.lvl_sn);
+  rc |= up_vec(sc, &d.panel_off, h.panel_off); rc |= up_vec(sc, &d.upd_off, h.upd_off);
+  rc |= dev_buf(sc, &sc->upd, (size_t)h.upd_total);
+  rc |= dev_buf(sc, &sc->uvec, h.rowidx.size());
+  rc |= dev_buf(sc, &sc->v, (size_t)n);
+  rc |= dev_buf(sc, &sc->W, (size_t)n * 8);
+  rc |= dev_buf(sc, &sc->mark, (size_t)h.nsuper);
+  if (rc) { sparse_chol_destroy(sc); return rc; }
+  (void)stream;
+  *out = sc;
+  return 0;
+}
+
+void sparse_chol_destroy(SparseChol *sc) {
+  if (!sc) return;
+  for (void *p : sc->allocs) cudaFree(p);
+  delete sc;
+}
+const SparseCholInfo *sparse_chol_info(const SparseChol *sc) { return &sc->info; }
+size_t sparse_chol_factor_doubles(const SparseChol *sc) { return (size_t)sc->h.nnzL; }
+
+// ------------------------------------------------------------------------------------------------
+// position of permuted row pr in the front of supernode s (binary search in R_s beyond the own columns)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int front_pos(const SpDev &d, int f, int ns, int ro, int nr, int pr) {
+  if (pr < f + ns) return pr - f;
+  int lo = 0, hi = nr;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.rowidx[ro + mid] < pr) lo = mid + 1; else hi = mid; }
+  return ns + lo;
+}
+
+// ================================================================================================
+// assembly of H = Q + A_J' Sigma_J A_J + beta I into the panels: one warp per (permuted) column
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_sp_assemble(SpDev d, double *panels, int with_Q, const int *__restrict__ Qp, const int *__restrict__ Qi,
+              const double *__restrict__ Qx, const int *__restrict__ Cp, const int *__restrict__ Ci,
+              const double *__restrict__ Cx, const int *__restrict__ Rp, const int *__restrict__ Rj,
+              const double *__restrict__ Rx, const int *__restrict__ active, const double *__restrict__ sigma, double beta) {
+  const int lane = threadIdx.x & 31;
+  const int pj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pj >= d.n) return;
+  const int j = d.perm[pj], s = d.sn_of_col[pj], f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s],
+            nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+  double *col = panels + d.panel_off[s] + (size_t)(pj - f) * nf;
+  for (int i = lane; i < nf; i += 32) col[i] = 0.0;
+  __syncwarp();
+  if (with_Q) {
+    for (int k = Qp[j] + lane; k < Qp[j + 1]; k += 32) {
+      const int pc = d.iperm[Qi[k]];
+      if (pc >= pj) col[front_pos(d, f, ns, ro, nr, pc)] = Qx[k];
+    }
+    __syncwarp();
+  }
+  if (active) {
+    for (int k = Cp[j]; k < Cp[j + 1]; k++) {
+      const int r = Ci[k];
+      if (!active[r]) continue;
+      const double v = sigma[r] * Cx[k];
+      for (int t = Rp[r] + lane; t < Rp[r + 1]; t += 32) {
+        const int pc = d.iperm[Rj[t]];
+        if (pc >= pj) col[front_pos(d, f, ns, ro, nr, pc)] += v * Rx[t];
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) col[pj - f] += beta;
+}
+
+int sparse_chol_assemble(SparseChol *sc, cudaStream_t s, double *panels, bool with_Q, const int *Qp, const int *Qi,
+                         const double *Qx, const int *Acsc_p, const int *Acsc_i, const double *Acsc_x, const int *Acsr_p,
+                         const int *Acsr_j, const double *Acsr_x, const int *active, const double *sigma, double beta) {
+  QB_LAUNCH(k_sp_assemble, cdiv(sc->d.n, 8), 256, 0, s, sc->d, panels, with_Q ? 1 : 0, Qp, Qi, Qx, Acsc_p, Acsc_i, Acsc_x,
+            Acsr_p, Acsr_j, Acsr_x, active, sigma, beta);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// numeric factorization, general path
+// ================================================================================================
+struct Front {
+  int s, f, ns, ro, nr, nf;
+  double *P, *U;
+};
+__device__ __forceinline__ Front load_front(const SpDev &d, double *panels, double *upd, int s) {
+  Front F;
+  F.s = s; F.f = d.first[s]; F.ns = d.first[s + 1] - F.f; F.ro = d.rows_off[s]; F.nr = d.rows_off[s + 1] - F.ro;
+  F.nf = F.ns + F.nr; F.P = panels + d.panel_off[s]; F.U = upd + d.upd_off[s];
+  return F;
+}
+__device__ __forceinline__ double *front_at(const Front &F, int i, int j) {   // i >= j in front index space
+  return (j < F.ns) ? F.P + (size_t)i + (size_t)j * F.nf : F.U + (size_t)(i - F.ns) + (size_t)(j - F.ns) * F.nr;
+}
+
+constexpr int kExtT = 16;   // target columns per CTA in the extend-add
+__global__ void __launch_bounds__(256) k_mf_extend(SpDev d, double *panels, double *upd, int lvl_begin) {
+  const Front F = load_front(d, panels, upd, d.lvl_sn[lvl_begin + blockIdx.x]);
+  const int c0 = blockIdx.y * kExtT, c1 = min(F.nf, c0 + kExtT);
+  if (c0 >= F.nf) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int tc = max(c0, F.ns) + warp; tc < c1; tc += nw)
+    for (int i = tc + lane; i < F.nf; i += 32) *front_at(F, i, tc) = 0.0;
+  __syncthreads();
+  for (int ch = d.child_ptr[F.s]; ch < d.child_ptr[F.s + 1]; ch++) {
+    const int c = d.child_idx[ch];
+    const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
+    const int *rel = d.rel + cro;
+    const double *Uc = upd + d.upd_off[c];
+    int a, b;
+    { int lo = 0, hi = cnr; while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < c0) lo = mid + 1; else hi = mid; } a = lo; }
+    { int lo = a, hi = cnr; while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < c1) lo = mid + 1; else hi = mid; } b = lo; }
+    for (int jc = a + warp; jc < b; jc += nw) {
+      const int tc = rel[jc];
+      for (int ic = jc + lane; ic < cnr; ic += 32) *front_at(F, rel[ic], tc) += Uc[(size_t)ic + (size_t)jc * cnr];
+    }
+    __syncthreads();
+  }
+}
+
+// 32 x 32 (w x w) Cholesky of the diagonal block kb of every front of the level: one warp per front, lane = row
+__global__ void __launch_bounds__(32) k_mf_diag(SpDev d, double *panels, int lvl_begin, int kb, int *info) {
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, nf = ns + d.rows_off[s + 1] - d.rows_off[s];
+  const int k0 = kb * 32;
+  if (k0 >= ns) return;
+  const int w = min(32, ns - k0), lane = threadIdx.x;
+  double *B = panels + d.panel_off[s] + (size_t)k0 + (size_t)k0 * nf;
+  double row[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) row[j] = (lane < w && j <= lane) ? B[(size_t)lane + (size_t)j * nf] : ((j == lane) ? 1.0 : 0.0);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double djj = __shfl_sync(0xffffffffu, row[j], j);
+    if (!(djj > 0.0) && j < w) bad = true;
+    const double l = sqrt(djj);
+    if (lane == j) row[j] = l; else if (lane > j) row[j] = row[j] / l;
+#pragma unroll
+    for (int jj = j + 1; jj < 32; jj++) {
+      const double ljj = __shfl_sync(0xffffffffu, row[j], jj);
+      if (lane >= jj) row[jj] = fma(-row[j], ljj, row[jj]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) if (lane < w && j <= lane) B[(size_t)lane + (size_t)j * nf] = row[j];
+  if (bad && lane == 0) atomicExch(info, 1 + f + k0);
+}
+
+// rows below diagonal block kb: X <- X * Lkk^{-T}, one thread per row
+__global__ void __launch_bounds__(128) k_mf_trsm(SpDev d, double *panels, int lvl_begin, int kb) {
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, nf = ns + d.rows_off[s + 1] - d.rows_off[s];
+  const int k0 = kb * 32;
+  if (k0 >= ns) return;
+  const int w = min(32, ns - k0);
+  const int i0 = k0 + w + blockIdx.y * 128;
+  if (i0 >= nf) return;
+  __shared__ double Ls[32][33];
+  double *P = panels + d.panel_off[s];
+  for (int t = threadIdx.x; t < 32 * 32; t += 128) {
+    const int r = t & 31, c = t >> 5;
+    Ls[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= nf) return;
+  double x[32];
+#pragma unroll
+  for (int t = 0; t < 32; t++) x[t] = (t < w) ? P[(size_t)i + (size_t)(k0 + t) * nf] : 0.0;
+#pragma unroll
+  for (int t = 0; t < 32; t++) {
+    double a = x[t];
+#pragma unroll
+    for (int u = 0; u < t; u++) a = fma(-x[u], Ls[t][u], a);
+    x[t] = a / Ls[t][t];
+  }
+#pragma unroll
+  for (int t = 0; t < 32; t++) if (t < w) P[(size_t)i + (size_t)(k0 + t) * nf] = x[t];
+}
+
+// trailing update after block kb: F(i, j) -= sum_t P(i, k0 + t) P(j, k0 + t), i >= j >= k0 + w; 64 x 64 tiles
+__global__ void __launch_bounds__(256) k_mf_syrk(SpDev d, double *panels, double *upd, int lvl_begin, int kb) {
+  if (blockIdx.z > blockIdx.y) return;   // tile (y, z): y = row tile, z = column tile, lower part only
+  const Front F = load_front(d, panels, upd, d.lvl_sn[lvl_begin + blockIdx.x]);
+  const int k0 = kb * 32;
+  if (k0 >= F.ns) return;
+  const int w = min(32, F.ns - k0), base = k0 + w;
+  const int i0 = base + blockIdx.y * 64, j0 = base + blockIdx.z * 64;
+  if (i0 >= F.nf || j0 >= F.nf) return;
+  __shared__ double As[32][65], Bs[32][65];
+  for (int t = threadIdx.x; t < 32 * 64; t += 256) {
+    const int r = t & 63, c = t >> 6;
+    As[c][r] = (c < w && i0 + r < F.nf) ? F.P[(size_t)(i0 + r) + (size_t)(k0 + c) * F.nf] : 0.0;
+    Bs[c][r] = (c < w && j0 + r < F.nf) ? F.P[(size_t)(j0 + r) + (size_t)(k0 + c) * F.nf] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // rows tx + 16 a, cols ty + 16 b
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int t = 0; t < 32; t++) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { av[a] = As[t][tx + 16 * a]; bv[a] = Bs[t][ty + 16 * a]; }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const int j = j0 + ty + 16 * b;
+    if (j >= F.nf) continue;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int i = i0 + tx + 16 * a;
+      if (i < F.nf && i >= j) { double *p = front_at(F, i, j); *p -= acc[a][b]; }
+    }
+  }
+}
+
+// ================================================================================================
+// numeric factorization, small fronts: whole front in shared memory (packed columns, ld = nf | 1)
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_mf_small(SpDev d, double *panels, double *upd, int lvl_begin, int *info) {
+  extern __shared__ double Fs[];
+  const Front F = load_front(d, panels, upd, d.lvl_sn[lvl_begin + blockIdx.x]);
+  const int nf = F.nf, ns = F.ns, ld = tri_ld(nf);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // load the panel, zero the update part (full square storage, lower part used)
+  for (int j = warp; j < nf; j += nw)
+    for (int i = j + lane; i < nf; i += 32) Fs[i + j * ld] = (j < ns) ? F.P[(size_t)i + (size_t)j * nf] : 0.0;
+  __syncthreads();
+  for (int ch = d.child_ptr[F.s]; ch < d.child_ptr[F.s + 1]; ch++) {
+    const int c = d.child_idx[ch];
+    const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
+    const int *rel = d.rel + cro;
+    const double *Uc = upd + d.upd_off[c];
+    for (int jc = warp; jc < cnr; jc += nw) {
+      const int tc = rel[jc];
+      for (int ic = jc + lane; ic < cnr; ic += 32) Fs[rel[ic] + tc * ld] += Uc[(size_t)ic + (size_t)jc * cnr];
+    }
+    __syncthreads();
+  }
+  // right-looking partial Cholesky of the first ns columns
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int k = 0; k < ns; k++) {
+    __syncthreads();
+    const double dkk = Fs[k + k * ld];
+    if (!(dkk > 0.0) && tid == 0) bad = 1 + F.f + k;
+    const double l = sqrt(dkk), linv = 1.0 / l;
+    __syncthreads();
+    for (int i = k + tid; i < nf; i += blockDim.x) Fs[i + k * ld] = (i == k) ? l : Fs[i + k * ld] * linv;
+    __syncthreads();
+    // trailing update: columns j > k, rows i >= j
+    for (int j = k + 1 + warp; j < nf; j += nw) {
+      const double ljk = Fs[j + k * ld];
+      if (ljk == 0.0) continue;
+      for (int i = j + lane; i < nf; i += 32) Fs[i + j * ld] = fma(-Fs[i + k * ld], ljk, Fs[i + j * ld]);
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < nf; j += nw) {
+    if (j < ns) { for (int i = j + lane; i < nf; i += 32) F.P[(size_t)i + (size_t)j * nf] = Fs[i + j * ld]; }
+    else { for (int i = j + lane; i < nf; i += 32) F.U[(size_t)(i - ns) + (size_t)(j - ns) * F.nr] = Fs[i + j * ld]; }
+  }
+  if (tid == 0 && bad) atomicExch(info, bad);
+}
+
+int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *info_dev) {
+  const SymHost &h = sc->h;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * tri_ld(kSmallMaxNf) * kSmallMaxNf)));
+    attr_set = true;
+  }
+  for (int l = 0; l < h.nlevels; l++) {
+    const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
+    const int mnf = h.lvl_max_nf[l], mns = h.lvl_max_ns[l];
+    if (cnt <= 0) continue;
+    if (mnf <= kSmallMaxNf) {
+      const size_t smem = sizeof(double) * (size_t)tri_ld(mnf) * mnf;
+      QB_LAUNCH(k_mf_small, cnt, mnf <= 32 ? 64 : (mnf <= 64 ? 128 : 256), smem, st, sc->d, panels, sc->upd, b, info_dev);
+      continue;
+    }
+    if (l > 0) { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
+    else { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
+    for (int kb = 0; kb * 32 < mns; kb++) {
+      QB_LAUNCH(k_mf_diag, cnt, 32, 0, st, sc->d, panels, b, kb, info_dev);
+      const int rest = mnf - kb * 32 - 1;   // rows below the block (upper bound over the level)
+      if (rest <= 0) continue;
+      { dim3 g(cnt, cdiv(rest, 128)); QB_LAUNCH(k_mf_trsm, g, 128, 0, st, sc->d, panels, b, kb); }
+      { const int T = cdiv(rest, 64); dim3 g(cnt, T, T); QB_LAUNCH(k_mf_syrk, g, 256, 0, st, sc->d, panels, sc->upd, b, kb); }
+    }
+  }
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// solves
+// ================================================================================================
+__global__ void k_sp_permute_in(SpDev d, const double *__restrict__ rhs, double *v, double sgn) {
+  const int pj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pj < d.n) v[pj] = sgn * rhs[d.perm[pj]];
+}
+__global__ void k_sp_permute_out(SpDev d, const double *__restrict__ v, double *out) {
+  const int pj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pj < d.n) out[d.perm[pj]] = v[pj];
+}
+
+// forward: L y = b.  f (shared, nf) = [b_s ; 0] + children's update vectors; solve the ns x ns triangle in 32-column
+// blocks; u_s = f[ns..) is handed to the parent.
+__global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restrict__ panels, double *v, double *uvec, int lvl_begin) {
+  extern __shared__ double fsh[];
+  __shared__ double blk[32][33];
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+  const double *P = panels + d.panel_off[s];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nf; i += blockDim.x) fsh[i] = (i < ns) ? v[f + i] : 0.0;
+  __syncthreads();
+  for (int ch = d.child_ptr[s]; ch < d.child_ptr[s + 1]; ch++) {
+    const int c = d.child_idx[ch];
+    const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
+    for (int i = tid; i < cnr; i += blockDim.x) fsh[d.rel[cro + i]] += uvec[cro + i];
+    __syncthreads();
+  }
+  for (int k0 = 0; k0 < ns; k0 += 32) {
+    const int w = min(32, ns - k0);
+    for (int t = tid; t < 32 * 32; t += blockDim.x) {
+      const int r = t & 31, c = t >> 5;
+      blk[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double x = (tid < w) ? fsh[k0 + tid] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const double xj = __shfl_sync(0xffffffffu, x, j) / blk[j][j];
+        if (tid == j) x = xj; else if (tid > j) x = fma(-blk[tid][j], xj, x);
+      }
+      if (tid < w) fsh[k0 + tid] = x;
+    }
+    __syncthreads();
+    for (int i = k0 + w + tid; i < nf; i += blockDim.x) {
+      double a = fsh[i];
+      for (int t = 0; t < w; t++) a = fma(-P[(size_t)i + (size_t)(k0 + t) * nf], fsh[k0 + t], a);
+      fsh[i] = a;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < nf; i += blockDim.x) { if (i < ns) v[f + i] = fsh[i]; else uvec[ro + i - ns] = fsh[i]; }
+}
+
+// backward: L' x = y.  f = [y_s ; x(R_s)]; per 32-column block (descending): subtract the column dots with everything
+// below the block (one warp per column), then the 32 x 32 transposed triangle.
+__global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restrict__ panels, double *v, int lvl_begin) {
+  extern __shared__ double fsh[];
+  __shared__ double blk[32][33];
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+  const double *P = panels + d.panel_off[s];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int i = tid; i < nf; i += blockDim.x) fsh[i] = (i < ns) ? v[f + i] : v[d.rowidx[ro + i - ns]];
+  __syncthreads();
+  const int nb = (ns + 31) / 32;
+  for (int kb = nb - 1; kb >= 0; kb--) {
+    const int k0 = kb * 32, w = min(32, ns - k0);
+    for (int t = tid; t < 32 * 32; t += blockDim.x) {
+      const int r = t & 31, c = t >> 5;
+      blk[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+    }
+    for (int t = warp; t < w; t += nw) {
+      const double *col = P + (size_t)(k0 + t) * nf;
+      double a = 0.0;
+      for (int i = k0 + w + lane; i < nf; i += 32) a = fma(col[i], fsh[i], a);
+      a = warp_sum(a);
+      if (lane == 0) fsh[k0 + t] -= a;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double x = (tid < w) ? fsh[k0 + tid] : 0.0;
+#pragma unroll
+      for (int j = 31; j >= 0; j--) {
+        const double xj = __shfl_sync(0xffffffffu, x, j) / blk[j][j];
+        if (tid == j) x = xj; else if (tid < j) x = fma(-blk[j][tid], xj, x);
+      }
+      if (tid < w) fsh[k0 + tid] = x;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < ns; i += blockDim.x) v[f + i] = fsh[i];
+}
+
+int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, const double *rhs, double *out, bool negate) {
+  const SymHost &h = sc->h;
+  const int n = sc->d.n;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (sizeof(double) * (size_t)h.max_nf > 200 * 1024) { fprintf(stderr, "[qpalm_b200] sparse solve: front of %d rows exceeds the shared-memory vector\n", h.max_nf); return 4; }
+  QB_LAUNCH(k_sp_permute_in, cdiv(n, 256), 256, 0, st, sc->d, rhs, sc->v, negate ? -1.0 : 1.0);
+  for (int l = 0; l < h.nlevels; l++) {
+    const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
+    if (cnt <= 0) continue;
+    const int mnf = h.lvl_max_nf[l];
+    QB_LAUNCH(k_mf_fwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+  }
+  for (int l = h.nlevels - 1; l >= 0; l--) {
+    const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
+    if (cnt <= 0) continue;
+    const int mnf = h.lvl_max_nf[l];
+    QB_LAUNCH(k_mf_bwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, b);
+  }
+  QB_LAUNCH(k_sp_permute_out, cdiv(n, 256), 256, 0, st, sc->d, sc->v, out);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// rank-k update / downdate (cholmod_updown replacement; recurrence of Modify/t_cholmod_updown_numkr.c:289-318 for LL')
+// ================================================================================================
+__global__ void k_ud_gather(SpDev d, const int *__restrict__ Rp, const int *__restrict__ Rj, const double *__restrict__ Rx,
+                            const int *__restrict__ list, const double *__restrict__ scale, int scale_by_row, int cnt,
+                            double *W, int *mark) {
+  const int c = blockIdx.x;
+  if (c >= cnt) return;
+  const int row = list[c];
+  const double sc = scale_by_row ? scale[row] : scale[c];
+  for (int t = Rp[row] + threadIdx.x; t < Rp[row + 1]; t += blockDim.x) {
+    const int pc = d.iperm[Rj[t]];
+    W[(size_t)pc + (size_t)c * d.n] = Rx[t] * sc;
+    int s = d.sn_of_col[pc];
+    while (s >= 0 && atomicExch(&mark[s], 1) == 0) s = d.sn_parent[s];
+  }
+}
+
+constexpr int kUdThreads = 512;
+__global__ void __launch_bounds__(kUdThreads) k_ud_sweep(SpDev d, double *panels, double *W, int *mark, int k, int sign, int *info) {
+  __shared__ double alpha[8], wj[8], gam[8];
+  __shared__ double winv_s, lnew_s;
+  __shared__ int skip_s, list[kUdThreads], nlist, wcount[kUdThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = d.n;
+  if (tid < 8) alpha[tid] = 1.0;
+  const double sg = (double)sign;
+  for (int base = 0; base < d.nsuper; base += kUdThreads) {
+    // ordered compaction of the marked supernodes of this chunk
+    const int sidx = base + tid;
+    const int flag = (sidx < d.nsuper) ? mark[sidx] : 0;
+    if (flag) mark[sidx] = 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag != 0);
+    if (lane == 0) wcount[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int wv = 0; wv < kUdThreads / 32; wv++) { if (wv < warp) off += wcount[wv]; tot += wcount[wv]; }
+    if (flag) list[off + __popc(bal & ((1u << lane) - 1u))] = sidx;
+    if (tid == 0) nlist = tot;
+    __syncthreads();
+    const int nl = nlist;
+    for (int q = 0; q < nl; q++) {
+      const int s = list[q];
+      const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+      double *P = panels + d.panel_off[s];
+      for (int lc = 0; lc < ns; lc++) {
+        const int j = f + lc;
+        if (tid == 0) {
+          bool any = false;
+          for (int r = 0; r < k; r++) { wj[r] = W[(size_t)j + (size_t)r * n]; any |= (wj[r] != 0.0); }
+          skip_s = any ? 0 : 1;
+          if (any) {
+            const double ljj = P[(size_t)lc + (size_t)lc * nf];
+            const double winv = 1.0 / ljj;
+            double dj = ljj * ljj;
+            for (int r = 0; r < k; r++) {
+              const double a = alpha[r] + sg * (wj[r] * wj[r]) / dj;
+              dj *= a;
+              gam[r] = -sg * wj[r] / dj;
+              dj /= alpha[r];
+              alpha[r] = a;
+              W[(size_t)j + (size_t)r * n] = 0.0;
+            }
+            if (!(dj > 0.0)) atomicExch(info, 1 + j);
+            const double lnew = sqrt(dj);
+            winv_s = winv; lnew_s = lnew;
+            P[(size_t)lc + (size_t)lc * nf] = lnew;
+          }
+        }
+        __syncthreads();
+        if (!skip_s) {
+          const double winv = winv_s, lnew = lnew_s;
+          for (int i = lc + 1 + tid; i < nf; i += kUdThreads) {
+            const int gi = (i < ns) ? f + i : d.rowidx[ro + i - ns];
+            double t = P[(size_t)i + (size_t)lc * nf] * winv;
+            for (int r = 0; r < k; r++) {
+              double wv = W[(size_t)gi + (size_t)r * n];
+              wv -= wj[r] * t;
+              t -= gam[r] * wv;
+              W[(size_t)gi + (size_t)r * n] = wv;
+            }
+            P[(size_t)i + (size_t)lc * nf] = t * lnew;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int sparse_chol_updown(SparseChol *sc, cudaStream_t st, double *panels, const int *Acsr_p, const int *Acsr_j,
+                       const double *Acsr_x, const int *list, const double *scale, bool scale_by_row, int cnt, int sign,
+                       int *info_dev) {
+  if (cnt <= 0) return 0;
+  if (cnt > 8) return 1;
+  QB_CUDA_TRY(cudaMemsetAsync(sc->W, 0, sizeof(double) * (size_t)sc->d.n * cnt, st));
+  QB_LAUNCH(k_ud_gather, cnt, 128, 0, st, sc->d, Acsr_p, Acsr_j, Acsr_x, list, scale, scale_by_row ? 1 : 0, cnt, sc->W, sc->mark);
+  QB_LAUNCH(k_ud_sweep, 1, kUdThreads, 0, st, sc->d, panels, sc->W, sc->mark, cnt, sign, info_dev);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// Gershgorin row sums of the (unfactored) symmetric matrix held in the panels; helpers for the tests
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_sp_abs_rowsums(SpDev d, const double *__restrict__ panels, double *out) {
+  const int lane = threadIdx.x & 31;
+  const int pj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pj >= d.n) return;
+  const int s = d.sn_of_col[pj], f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nf = ns + d.rows_off[s + 1] - ro;
+  const int lc = pj - f;
+  const double *col = panels + d.panel_off[s] + (size_t)lc * nf;
+  double acc = 0.0;
+  for (int i = lc + lane; i < nf; i += 32) {
+    const double a = fabs(col[i]);
+    acc += a;
+    if (i > lc && a != 0.0) atomicAdd(&out[(i < ns) ? f + i : d.rowidx[ro + i - ns]], a);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(&out[pj], acc);
+}
+int sparse_chol_abs_rowsums(SparseChol *sc, cudaStream_t st, const double *panels, double *out_n) {
+  QB_CUDA_TRY(cudaMemsetAsync(out_n, 0, sizeof(double) * (size_t)sc->d.n, st));
+  QB_LAUNCH(k_sp_abs_rowsums, cdiv(sc->d.n, 8), 256, 0, st, sc->d, panels, out_n);
+  QB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int sparse_chol_download(SparseChol *sc, cudaStream_t st, const double *panels, double *L_host, long long *perm_host) {
+  const SymHost &h = sc->h;
+  const int n = h.n;
+  std::vector<double> P((size_t)h.nnzL);
+  QB_CUDA_TRY(cudaStreamSynchronize(st));
+  QB_CUDA_TRY(cudaMemcpy(P.data(), panels, sizeof(double) * P.size(), cudaMemcpyDeviceToHost));
+  memset(L_host, 0, sizeof(double) * (size_t)n * n);
+  for (int s = 0; s < h.nsuper; s++) {
+    const int f = h.sn_first[s], ns = h.sn_first[s + 1] - f, ro = h.rows_off[s], nr = h.rows_off[s + 1] - ro, nf = ns + nr;
+    const double *p = P.data() + h.panel_off[s];
+    for (int lc = 0; lc < ns; lc++)
+      for (int i = lc; i < nf; i++) {
+        const int gi = i < ns ? f + i : h.rowidx[ro + i - ns];
+        L_host[(size_t)gi + (size_t)(f + lc) * n] = p[(size_t)i + (size_t)lc * nf];
+      }
+  }
+  for (int i = 0; i < n; i++) perm_host[i] = h.perm[i];
+  return 0;
+}
+
+}  // namespace qb

@@ -1,5 +1,6 @@
 #!/bin/bash
-# One gpurun call: parity tests, smoke, bench (both arms), kernel launch lists under ncu.  Logs go to gpurun_out/.
+# One gpurun call: parity tests, smoke, bench (both arms), kernel launch lists under ncu, ncu --set full of the two
+# dominant kernels.  Logs go to gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt
@@ -13,4 +14,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --
    python bench.py --steps 1 --warmup 1 --no-dense --no-cpu > gpurun_out/ncu_batch.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_dense.csv \
    python bench.py --workload dense --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_dense.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:kbp_solve -s 1 -c 1 -f -o gpurun_out/full_kbp_solve \
+   python bench.py --steps 1 --warmup 1 --no-dense --no-cpu > gpurun_out/ncu_full_batch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dgemm_nt -s 200 -c 1 -f -o gpurun_out/full_k_dgemm_nt \
+   python bench.py --workload dense --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full_dense.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; tail -2 gpurun_out/bench.log; tail -2 gpurun_out/bench_ref.log; tail -2 gpurun_out/bench_dense.log
+ls -la gpurun_out
