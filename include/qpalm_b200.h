@@ -206,6 +206,9 @@ typedef struct {
   double  device_ms_factor;     /* CUDA-event time spent in refactorizations                           */
   double  device_ms_updown;
   double  device_ms_total;      /* CUDA-event time of the whole qpalm_solve                            */
+  int64_t sparse_factor_nnz;    /* entries of the supernodal factor (0: the dense Newton path is in use)  */
+  int64_t sparse_supernodes;
+  int64_t sparse_levels;        /* assembly-tree levels = launches-in-sequence of one factorization pass */
 } QPALMB200Stats;
 int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *out);
 /* Selective per-kernel CUDA-event timing of the library's own launches (csrc/prof.cu): `patterns` is a comma-separated
@@ -259,6 +262,24 @@ int qpalm_b200_newton_solve(const solver_sparse *Q, const solver_sparse *A, cons
  * ldlupdate_entering_constraints / ldldowndate_leaving_constraints (solver_interface.c:407-441).
  * L: n x n column-major lower factor (in/out);  W: n x k column-major;  update != 0 => L L' + W W'. */
 int qpalm_b200_updown(c_int n, c_int k, c_float *L, const c_float *W, c_int update);
+
+/* Sparse Newton system -- replaces, for problems whose Schur complement Q + A'A stays sparse, cholmod_analyze +
+ * cholmod_factorize (ldlchol / ldlcholQAtsigmaA, solver_interface.c:319-405), cholmod_updown (:407-441) and cholmod_solve
+ * (:505-519) with a supernodal multifrontal Cholesky (csrc/sparse.cu).
+ * symbolic_*: the one-time HOST-side analysis (fill-reducing ordering, etree, supernodes, assembly-tree levels); no CUDA call,
+ * usable without a GPU.  symbolic_array copies one structure array ("perm", "iperm", "sn_first", "sn_of_col", "rows_off",
+ * "rowidx", "rel", "sn_parent", "child_ptr", "child_idx", "lvl_ptr", "lvl_sn", "panel_off", "upd_off") and returns its length.
+ * sparse_newton: factor Q + A_J' Sigma_J A_J + beta I for J = active, then rank-update with the rows `enter` and rank-downdate
+ * with the rows `leave` (each scaled by sqrt(sigma)), then d = (L L')^{-1} rhs.  L_out (n x n column-major, PERMUTED order) and
+ * perm_out (perm[new] = old) are optional; rowsums_out[0] (optional) receives the Gershgorin bound of A_J' Sigma_J A_J. */
+typedef struct QPALMB200Symbolic QPALMB200Symbolic;
+QPALMB200Symbolic *qpalm_b200_symbolic_analyze(const solver_sparse *Q, const solver_sparse *A);
+int   qpalm_b200_symbolic_info(const QPALMB200Symbolic *S, c_int out8[8], double *flops);
+c_int qpalm_b200_symbolic_array(const QPALMB200Symbolic *S, const char *name, c_int *out, c_int cap);
+void  qpalm_b200_symbolic_free(QPALMB200Symbolic *S);
+int qpalm_b200_sparse_newton(const solver_sparse *Q, const solver_sparse *A, const c_float *sigma, const c_int *active,
+        c_float beta, const c_float *rhs, c_float *d, c_float *L_out, c_int *perm_out, const c_int *enter, c_int nb_enter,
+        const c_int *leave, c_int nb_leave, c_float *rowsums_out);
 
 /* lambda_min estimate -- replaces lobpcg (nonconvex.c:29-168).  x0 is the (un-normalised) start
  * vector the reference draws with rand(); returns the under-estimate the reference returns. */

@@ -133,7 +133,8 @@ class QPALMB200Stats(C.Structure):
                 ("updown_rank_sum", C.c_int64), ("spmv_calls", C.c_int64),
                 ("algorithmic_bytes", C.c_double), ("dense_flops", C.c_double),
                 ("device_ms_factor", C.c_double), ("device_ms_updown", C.c_double),
-                ("device_ms_total", C.c_double)]
+                ("device_ms_total", C.c_double),
+                ("sparse_factor_nnz", C.c_int64), ("sparse_supernodes", C.c_int64), ("sparse_levels", C.c_int64)]
 
 
 # --------------------------------------------------------------------------------------------

@@ -324,7 +324,7 @@ static void collect(Engine *e, Pending &p) {
   if (!p.kind) return;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->evs0, e->evs1) == cudaSuccess) {
-    if (p.kind == 1) { e->ms_factor += ms; e->last_refactor_ms = ms; } else e->ms_updown += ms;
+    if (p.kind == 1) { e->ms_factor += ms; e->last_refactor_ms = ms; } else { e->ms_updown += ms; e->last_updown_ms = ms; }
   }
   p.kind = 0;
 }
@@ -382,9 +382,13 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 // (~30 us + ~12 us per rank each, measured on B200), a refactorisation is DMMA-bound; the update path is taken
 // only when it is predicted to be cheaper than the last measured refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
-  if (k <= 0 || k > e->updown_max_rank) return false;
+  if (k <= 0 || k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->sh_world > 1) return false;   // row-sharded: the entering rows live on different ranks; refactorise (allreduced H)
   if (e->updown_force) return true;
+  if (e->sp) {   // sparse factor: k sweeps of <= 8 ranks along etree paths; measured cost of the last one vs the last refactorisation
+    const double t_sweep = e->last_updown_ms > 0 ? e->last_updown_ms : 0.0;   // unknown yet: try it once
+    return t_sweep * ((k + 7) / 8) < (e->last_refactor_ms > 0 ? e->last_refactor_ms : 1e30);
+  }
   const double t_ud = (e->npad / 32.0) * (0.030 + 0.012 * k);
   const double t_rf = e->last_refactor_ms > 0 ? e->last_refactor_ms : 1e-9 * ((double)e->n * e->n * e->n / 3.0) / 8.0 + 0.2;
   return t_ud < t_rf;
@@ -444,7 +448,7 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
   const bool prox0 = st->proximal != 0;
   (void)prox0;
   if (st->enable_dual_termination) {   // qpalm.c:459-472
-    if (!e->LQ) { QP_EPRINT("enable_dual_termination must be set at qpalm_setup time"); update_status(work->info, QPALM_ERROR); return; }
+    if (!e->LQ && !e->spLQ) { QP_EPRINT("enable_dual_termination must be set at qpalm_setup time"); update_status(work->info, QPALM_ERROR); return; }
     factor_Q_for_dual(e);
     work->info->dual_objective = dual_objective_now(work);
   } else work->info->dual_objective = QPALM_NULL;
@@ -732,5 +736,8 @@ extern "C" int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *
   out->refactor_active_sum = e->refactor_active_sum; out->updown_calls = e->n_updown; out->updown_rank_sum = e->updown_rank_sum;
   out->spmv_calls = e->n_spmv; out->algorithmic_bytes = e->alg_bytes; out->dense_flops = e->dense_flops;
   out->device_ms_factor = e->ms_factor; out->device_ms_updown = e->ms_updown; out->device_ms_total = e->ms_total;
+  out->sparse_factor_nnz = e->sp ? sparse_chol_info(e->sp)->nnzL : 0;
+  out->sparse_supernodes = e->sp ? sparse_chol_info(e->sp)->nsuper : 0;
+  out->sparse_levels = e->sp ? sparse_chol_info(e->sp)->nlevels : 0;
   return 0;
 }

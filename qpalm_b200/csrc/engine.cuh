@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "dense.cuh"
+#include "sparse.cuh"
 
 namespace qb {
 
@@ -82,6 +83,9 @@ struct Engine {
   // Newton system
   double *H = nullptr, *L = nullptr, *invdiag = nullptr, *W = nullptr, *LQ = nullptr, *invdiagQ = nullptr;
   int wcols = 0;                      // columns of the gather panel W (multiple of 16)
+  // sparse Newton system (sparse.cuh): supernodal factor instead of the dense H / L when the Schur complement stays sparse
+  SparseChol *sp = nullptr;
+  double *spL = nullptr, *spLQ = nullptr;   // numeric factors in the panel layout (Newton system; Q alone for the dual objective)
   double *ud_coef = nullptr;
   // reductions / scalars
   double *partials = nullptr; int partial_blocks = 0;
@@ -96,6 +100,7 @@ struct Engine {
   // tunables
   int updown_max_rank = 8;           // one sweep of the rank-k kernel
   int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
+  double last_updown_ms = -1.0;      // CUDA-event time of the most recent update/downdate call (sparse cost model)
   double last_refactor_ms = -1.0;    // CUDA-event time of the most recent refactorisation (cost model input)
   //   // device cost model: beyond this a (incremental) refactorisation is cheaper
 };

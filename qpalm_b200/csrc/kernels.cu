@@ -5,6 +5,7 @@
 // compiled with -fmad=false, so Axys, z, the active set, alpha, delta and the breakpoints s = alpha/delta
 // are bit-identical to the reference at identical inputs.
 #include "engine.cuh"
+#include <vector>
 #include <math.h>
 #include <string.h>
 
@@ -514,7 +515,24 @@ static int syrk_list(Engine *e, double *dst, const int *list, const double *scal
 
 // ldlcholQAtsigmaA / ldlchol(Q)  (solver_interface.c:319-405): assemble H (incrementally when cheaper),
 // L <- chol(H + beta I)
+// sparse problems: H is assembled straight into the supernodal panels (always from scratch: the assembly is
+// O(sum_active nnz_row^2), negligible next to the factorization) and factorized level by level (sparse.cu)
+static int sparse_refactor(Engine *e, bool with_constraints, double beta, int nb_active) {
+  QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
+  const bool wc = with_constraints && e->m > 0;
+  if (int r = sparse_chol_assemble(e->sp, e->stream, e->spL, true, e->Q_csr.p, e->Q_csr.i, e->Q_csr.x, e->A_csc.p, e->A_csc.i,
+                                   e->A_csc.x, e->A_csr.p, e->A_csr.i, e->A_csr.x, wc ? e->active : nullptr, e->sigma, beta)) return r;
+  if (int r = sparse_chol_factor(e->sp, e->stream, e->spL, e->info_dev)) return r;
+  QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
+  const SparseCholInfo *I = sparse_chol_info(e->sp);
+  e->n_refactor++; e->refactor_active_sum += wc ? nb_active : 0;
+  e->dense_flops += I->flops;
+  e->alg_bytes += 12.0 * (double)I->nnzS + 2.0 * 8.0 * (double)I->nnzL;   // B_H + B_L (read H, write + read L)
+  return 0;
+}
+
 int step_newton_refactor(Engine *e, bool with_constraints, bool from_scratch, double beta, int nb_active) {
+  if (e->sp) return sparse_refactor(e, with_constraints, beta, nb_active);
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
   if (!with_constraints || e->m == 0) {
     if (int r = init_lower_from_Q(e, e->L)) return r;
@@ -560,6 +578,13 @@ int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
     const int cnt = pass == 0 ? nb_enter : nb_leave;
     for (int off = 0; off < cnt; off += 8) {
       const int k = cnt - off < 8 ? cnt - off : 8;
+      if (e->sp) {
+        if (int r = sparse_chol_updown(e->sp, e->stream, e->spL, e->A_csr.p, e->A_csr.i, e->A_csr.x, list + off, e->sqrt_sigma,
+                                       true, k, pass == 0 ? +1 : -1, e->info_dev)) return r;
+        e->n_updown++; e->updown_rank_sum += k;
+        e->alg_bytes += 2.0 * 12.0 * (double)sparse_chol_info(e->sp)->nnzL;
+        continue;
+      }
       if (int r = gather_rows(e, list + off, e->sqrt_sigma, true, k, 8)) return r;
       if (int r = chol_updown(e->stream, e->npad, e->L, e->ld, e->W, e->ld, k, pass == 0 ? +1 : -1, e->ud_coef, e->info_dev)) return r;
       e->n_updown++; e->updown_rank_sum += k;
@@ -567,7 +592,7 @@ int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
       e->alg_bytes += 2.0 * 8.0 * (double)e->n * (e->n + 1) / 2;
     }
   }
-  if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r;
+  if (!e->sp) { if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r; }
   QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
   return 0;
 }
@@ -577,12 +602,18 @@ int sigma_changed_update(Engine *e, int nb_changed) {
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
   for (int off = 0; off < nb_changed; off += 8) {
     const int k = nb_changed - off < 8 ? nb_changed - off : 8;
+    if (e->sp) {
+      if (int r = sparse_chol_updown(e->sp, e->stream, e->spL, e->A_csr.p, e->A_csr.i, e->A_csr.x, e->changed + off, e->w_pos + off,
+                                     false, k, +1, e->info_dev)) return r;
+      e->n_updown++; e->updown_rank_sum += k;
+      continue;
+    }
     if (int r = gather_rows(e, e->changed + off, e->w_pos + off, false, k, 8)) return r;
     if (int r = chol_updown(e->stream, e->npad, e->L, e->ld, e->W, e->ld, k, +1, e->ud_coef, e->info_dev)) return r;
     e->n_updown++; e->updown_rank_sum += k;
     e->dense_flops += 2.0 * k * (double)e->n * e->n;
   }
-  if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r;
+  if (!e->sp) { if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r; }
   QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
   return 0;
 }
@@ -593,6 +624,11 @@ __global__ void k_neg_to_pad(int n, int npad, const double *__restrict__ src, do
 }
 // ldlsolveLD_neg_dphi (solver_interface.c:505-519)
 int step_newton_solve(Engine *e) {
+  if (e->sp) {
+    e->alg_bytes += 2.0 * 12.0 * (double)sparse_chol_info(e->sp)->nnzL;
+    e->dense_flops += 4.0 * (double)sparse_chol_info(e->sp)->nnzL;
+    return sparse_chol_solve(e->sp, e->stream, e->spL, e->dphi, e->d, true);
+  }
   QB_LAUNCH(k_neg_to_pad, cdiv(e->npad, 256), 256, 0, e->stream, e->n, e->npad, e->dphi, e->vpad);
   if (int r = chol_solve(e->stream, e->npad, e->L, e->ld, e->invdiag, e->vpad)) return r;
   e->dense_flops += 2.0 * (double)e->n * e->n;
@@ -954,6 +990,17 @@ __global__ void __launch_bounds__(kRedThreads) k_max_reduce(int n, const double 
   block_partial<RED_MAX>(mx, scratch, partials, slot);
 }
 int step_gershgorin_AtSA(Engine *e, double *ub_host) {
+  if (e->sp) {   // A_J' Sigma_J A_J assembled into the factor's panels (the caller refactorises afterwards)
+    if (int r = sparse_chol_assemble(e->sp, e->stream, e->spL, false, e->Q_csr.p, e->Q_csr.i, e->Q_csr.x, e->A_csc.p, e->A_csc.i,
+                                     e->A_csc.x, e->A_csr.p, e->A_csr.i, e->A_csr.x, e->active, e->sigma, 0.0)) return r;
+    if (int r = sparse_chol_abs_rowsums(e->sp, e->stream, e->spL, e->tmp_n)) return r;
+    const int g = red_grid(e->n);
+    QB_LAUNCH(k_max_reduce, g, kRedThreads, 0, e->stream, e->n, e->tmp_n, e->partials, S_TMP4);
+    finalize(e, {S_TMP4}, g);
+    if (int r = sync_scalars(e)) return r;
+    *ub_host = e->scal_host[S_TMP4];
+    return 0;
+  }
   QB_CUDA_TRY(cudaMemsetAsync(e->L, 0, sizeof(double) * (size_t)e->ld * e->npad, e->stream));
   // temporary lists of the committed active set; the H record is left untouched (separate scratch arrays)
   QB_LAUNCH(k_build_lists, 1, kListThreads, 0, e->stream, e->m, 1, 1, e->active_cand, e->active, e->active_old, e->sigma,
@@ -987,6 +1034,12 @@ k_dual_obj(int n, int m, const double *__restrict__ rhs, const double *__restric
   block_partial<RED_SUM>(sup, scratch, partials, S_TMP1);
 }
 int factor_Q_for_dual(Engine *e) {
+  if (e->sp) {
+    if (!e->spLQ) return 1;
+    if (int r = sparse_chol_assemble(e->sp, e->stream, e->spLQ, true, e->Q_csr.p, e->Q_csr.i, e->Q_csr.x, e->A_csc.p, e->A_csc.i,
+                                     e->A_csc.x, e->A_csr.p, e->A_csr.i, e->A_csr.x, nullptr, e->sigma, 0.0)) return r;
+    return sparse_chol_factor(e->sp, e->stream, e->spLQ, e->info_dev);
+  }
   if (!e->LQ) return 1;
   if (int r = init_lower_from_Q(e, e->LQ)) return r;
   QB_LAUNCH(k_add_diag_pad, cdiv(e->npad, 256), 256, 0, e->stream, e->n, e->npad, e->LQ, e->ld, 0.0);
@@ -994,7 +1047,8 @@ int factor_Q_for_dual(Engine *e) {
 }
 int step_dual_objective(Engine *e, double *val_host) {
   QB_LAUNCH(k_add_to_pad, cdiv(e->npad, 256), 256, 0, e->stream, e->n, e->npad, e->Aty, e->q, e->vpad, e->tmp_n);
-  if (int r = chol_solve(e->stream, e->npad, e->LQ, e->ld, e->invdiagQ, e->vpad)) return r;
+  if (e->sp) { if (int r = sparse_chol_solve(e->sp, e->stream, e->spLQ, e->tmp_n, e->vpad, false)) return r; }
+  else if (int r = chol_solve(e->stream, e->npad, e->LQ, e->ld, e->invdiagQ, e->vpad)) return r;
   const int len = e->n > e->m ? e->n : e->m;
   const int g = red_grid(len);
   QB_LAUNCH(k_dual_obj, g, kRedThreads, 0, e->stream, e->n, e->m, e->tmp_n, e->vpad, e->y, e->bmin, e->bmax, e->partials);
@@ -1392,8 +1446,11 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   if (int r = init_slot_ops()) return r;
   e->n = n; e->m = m; e->npad = round_up(n > 0 ? n : 1, kPanel); e->ld = e->npad;
   const long long nnzA = m > 0 ? Ap[n] : 0;
+  std::vector<int> hA_cp, hA_ci, hA_rp, hA_rj;   // host int32 copies of sparse A for the symbolic analysis
   // ---- A ----
-  e->A_dense = (m > 0) && ((double)nnzA >= 0.25 * (double)m * (double)n);
+  const char *newton_mode = getenv("QPALM_B200_NEWTON");   // dense | sparse: overrides the density heuristics (tests)
+  const bool force_sparse = newton_mode && !strcmp(newton_mode, "sparse"), force_dense = newton_mode && !strcmp(newton_mode, "dense");
+  e->A_dense = !force_sparse && (m > 0) && ((double)nnzA >= 0.25 * (double)m * (double)n);
   e->m_lo = 0; e->m_loc = m; e->m_cap = m;
   if (e->A_dense && shard_world() > 1 && m >= shard_world()) {   // row-sharded dense QP (shard.cu): keep only this rank's rows of A
     e->sh_world = shard_world(); e->sh_rank = shard_rank();
@@ -1434,12 +1491,13 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     for (int i = 0; i < m; i++) rp[i + 2] += rp[i + 1];
     for (int j = 0; j < n; j++) for (long long k = Ap[j]; k < Ap[j + 1]; k++) { const int dpos = rp[Ai[k] + 1]++; rj[dpos] = j; rx[dpos] = Ax[k]; }
     if (int r = upload_sparse(&e->A_csr, m, n, rp, rj, rx)) return r;
+    hA_cp.assign(cp, cp + n + 1); hA_ci.assign(ci, ci + nnzA); hA_rp.assign(rp + 0, rp + m + 1); hA_rj.assign(rj, rj + nnzA);
     free(cp); free(ci); free(rp); free(rj); free(rx);
   }
   // ---- Q (only row >= col entries are read: stype -1) ----
   long long nnzL = 0;
   for (int j = 0; j < n; j++) for (long long k = Qp[j]; k < Qp[j + 1]; k++) if (Qi[k] >= j) nnzL++;
-  e->Q_dense = (double)nnzL >= 0.25 * 0.5 * (double)n * ((double)n + 1.0);
+  e->Q_dense = !force_sparse && (double)nnzL >= 0.25 * 0.5 * (double)n * ((double)n + 1.0);
   if (e->Q_dense) {
     if (int r = dev_alloc((void **)&e->Qd, sizeof(double) * (size_t)n * n)) return r;
     if (nnzL == (long long)n * (n + 1) / 2 && Qp[n] == nnzL) {   // packed dense lower triangle: expand on the device
@@ -1500,20 +1558,41 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   rc |= dev_alloc((void **)&e->rs_hist, sizeof(unsigned int) * 256 * (size_t)e->rs_tiles);
   if (rc) return rc;
   // ---- Newton system ----
-  const size_t LL = (size_t)e->ld * e->npad;
+  // sparse problems whose Schur complement Q + A'A stays sparse: supernodal factor (sparse.cu) instead of dense H / L.
+  {
+    if (!force_dense && !e->A_dense && !e->Q_dense && e->sh_world == 1 && n > 0) {
+      if (hA_cp.empty()) { hA_cp.assign((size_t)n + 1, 0); hA_rp.assign((size_t)m + 1, 0); }
+      if (int r = sparse_chol_analyze(&e->sp, n, m, hA_cp.data(), hA_ci.data(), hA_rp.data(), hA_rj.data(), Qp, Qi, force_sparse, e->stream)) return r;
+      if (e->sp) {
+        const SparseCholInfo *I = sparse_chol_info(e->sp);
+        if (getenv("QPALM_B200_VERBOSE"))
+          fprintf(stderr, "[qpalm_b200] sparse Newton path: n=%d nnz(S)=%lld nnz(L)=%lld (%.2f%% of dense) supernodes=%d levels=%d "
+                          "max front %d x %d, %.3g flop/factorization\n", n, I->nnzS, I->nnzL, 100.0 * I->nnzL / (0.5 * n * (n + 1.0)),
+                  I->nsuper, I->nlevels, I->max_nf, I->max_ns, I->flops);
+      }
+    }
+  }
+  const size_t LL = e->sp ? 1 : (size_t)e->ld * e->npad;
   size_t free_b = 0, total_b = 0;
   QB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  e->wcols = round_up(m < 16 ? 16 : (m > 2048 ? 2048 : m), 16);
-  const size_t need = sizeof(double) * (LL * (need_LQ ? 3 : 2) + (size_t)e->ld * e->wcols + (size_t)e->npad * kPanel * 2);
+  e->wcols = e->sp ? 16 : round_up(m < 16 ? 16 : (m > 2048 ? 2048 : m), 16);
+  if (e->sp) {
+    rc |= dv(&e->spL, sparse_chol_factor_doubles(e->sp));
+    if (need_LQ) rc |= dv(&e->spLQ, sparse_chol_factor_doubles(e->sp));
+    if (rc) return rc;
+  }
+  const size_t need = e->sp ? 0 : sizeof(double) * (LL * (need_LQ ? 3 : 2) + (size_t)e->ld * e->wcols + (size_t)e->npad * kPanel * 2);
   if (need + (256u << 20) > free_b) {
     fprintf(stderr, "[qpalm_b200] dense Newton path needs %.1f GB for n=%d but only %.1f GB of HBM is free "
-                    "(the supernodal sparse path is not built yet)\n", need / 1e9, n, free_b / 1e9);
+                    "(and the union pattern Q + A'A is too dense for the supernodal sparse path)\n", need / 1e9, n, free_b / 1e9);
     return 2;
   }
-  rc |= dv(&e->H, LL); rc |= dv(&e->L, LL); rc |= dv(&e->invdiag, (size_t)e->npad * kPanel);
-  rc |= dv(&e->W, (size_t)e->ld * e->wcols);
+  if (!e->sp) {
+    rc |= dv(&e->H, LL); rc |= dv(&e->L, LL); rc |= dv(&e->invdiag, (size_t)e->npad * kPanel);
+    rc |= dv(&e->W, (size_t)e->ld * e->wcols);
+    if (need_LQ) { rc |= dv(&e->LQ, LL); rc |= dv(&e->invdiagQ, (size_t)e->npad * kPanel); }
+  }
   rc |= dv(&e->ud_coef, 2 * 32 * 18 + 16);
-  if (need_LQ) { rc |= dv(&e->LQ, LL); rc |= dv(&e->invdiagQ, (size_t)e->npad * kPanel); }
   rc |= dv(&e->partials, (size_t)S_COUNT * kRedBlocks);
   {
     const int rowctas = cdiv(n > 0 ? n : 1, 128);
@@ -1546,8 +1625,9 @@ void engine_destroy(Engine *e) {
                   e->tmp_n2, e->tmp_m, e->vpad, e->active, e->active_old, e->active_cand, e->enter, e->leave, e->changed,
                   e->list_pos, e->list_neg, e->w_pos, e->w_neg, e->activeH, e->sigmaH, e->ls_key[0], e->ls_key[1],
                   e->ls_val[0], e->ls_val[1], e->ls_da, e->ls_db, e->rs_hist, e->H, e->L, e->invdiag, e->W, e->LQ,
-                  e->invdiagQ, e->ud_coef, e->partials, e->gemv_partials, e->scal_dev, e->info_dev};
+                  e->invdiagQ, e->ud_coef, e->partials, e->gemv_partials, e->scal_dev, e->info_dev, e->spL, e->spLQ};
   for (void *p : ptrs) if (p) cudaFree(p);
+  sparse_chol_destroy(e->sp);
   if (e->scal_host) cudaFreeHost(e->scal_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);

@@ -3,9 +3,11 @@
 // "at identical iterates" against the oracle and the reference.
 #include "../../include/qpalm_b200.h"
 #include "engine.cuh"
+#include "sparse_host.h"
 #include <math.h>
 #include <string.h>
 #include <vector>
+#include <string>
 
 using namespace qb;
 
@@ -233,6 +235,101 @@ extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *
   QB_CUDA_TRY(cudaMemcpy(&info, e->info_dev, sizeof(int), cudaMemcpyDeviceToHost));
   engine_destroy(e);
   return rc ? rc : (info ? 1000 : 0);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// sparse Newton system (sparse.cuh): host-only symbolic analysis + device factor / update / solve
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HostA { std::vector<int> cp, ci, rp, rj; };
+void host_csr_csc(const solver_sparse *A, int n, HostA *h) {
+  const int m = A ? (int)A->nrow : 0;
+  h->cp.assign((size_t)n + 1, 0); h->rp.assign((size_t)m + 1, 0);
+  if (!A || m == 0) return;
+  const long long *Ap = (const long long *)A->p, *Ai = (const long long *)A->i;
+  const long long nnz = Ap[n];
+  h->ci.resize(nnz); h->rj.resize(nnz);
+  for (int j = 0; j <= n; j++) h->cp[j] = (int)Ap[j];
+  for (long long k = 0; k < nnz; k++) { h->ci[k] = (int)Ai[k]; h->rp[Ai[k] + 1]++; }
+  for (int i = 0; i < m; i++) h->rp[i + 1] += h->rp[i];
+  std::vector<int> fill(h->rp.begin(), h->rp.end() - 1);
+  for (int j = 0; j < n; j++) for (long long k = Ap[j]; k < Ap[j + 1]; k++) h->rj[fill[Ai[k]]++] = j;
+}
+}  // namespace
+
+struct QPALMB200Symbolic { SymHost h; };
+
+extern "C" QPALMB200Symbolic *qpalm_b200_symbolic_analyze(const solver_sparse *Q, const solver_sparse *A) {
+  const int n = (int)Q->ncol, m = A ? (int)A->nrow : 0;
+  HostA ha; host_csr_csc(A, n, &ha);
+  QPALMB200Symbolic *S = new QPALMB200Symbolic();
+  if (symbolic_analyze(n, m, ha.cp.data(), ha.ci.data(), ha.rp.data(), ha.rj.data(), (const long long *)Q->p, (const long long *)Q->i,
+                       true, &S->h) != 0) { delete S; return nullptr; }
+  return S;
+}
+extern "C" int qpalm_b200_symbolic_info(const QPALMB200Symbolic *S, c_int out8[8], double *flops) {
+  const SymHost &h = S->h;
+  out8[0] = h.n; out8[1] = h.nsuper; out8[2] = h.nlevels; out8[3] = h.max_ns; out8[4] = h.max_nf; out8[5] = h.nnzS; out8[6] = h.nnzL;
+  out8[7] = h.upd_total;
+  if (flops) *flops = h.flops;
+  return 0;
+}
+extern "C" c_int qpalm_b200_symbolic_array(const QPALMB200Symbolic *S, const char *name, c_int *out, c_int cap) {
+  const SymHost &h = S->h;
+  const std::vector<int> *v = nullptr; const std::vector<long long> *w = nullptr;
+  const std::string nm(name);
+  if (nm == "perm") v = &h.perm; else if (nm == "iperm") v = &h.iperm; else if (nm == "sn_first") v = &h.sn_first;
+  else if (nm == "sn_of_col") v = &h.sn_of_col; else if (nm == "rows_off") v = &h.rows_off; else if (nm == "rowidx") v = &h.rowidx;
+  else if (nm == "rel") v = &h.rel; else if (nm == "sn_parent") v = &h.sn_parent; else if (nm == "child_ptr") v = &h.child_ptr;
+  else if (nm == "child_idx") v = &h.child_idx; else if (nm == "lvl_ptr") v = &h.lvl_ptr; else if (nm == "lvl_sn") v = &h.lvl_sn;
+  else if (nm == "panel_off") w = &h.panel_off; else if (nm == "upd_off") w = &h.upd_off;
+  else return -1;
+  const c_int len = v ? (c_int)v->size() : (c_int)w->size();
+  if (out) for (c_int i = 0; i < len && i < cap; i++) out[i] = v ? (c_int)(*v)[i] : (c_int)(*w)[i];
+  return len;
+}
+extern "C" void qpalm_b200_symbolic_free(QPALMB200Symbolic *S) { delete S; }
+
+extern "C" int qpalm_b200_sparse_newton(const solver_sparse *Q, const solver_sparse *A, const c_float *sigma, const c_int *active,
+        c_float beta, const c_float *rhs, c_float *d, c_float *L_out, c_int *perm_out, const c_int *enter, c_int nb_enter,
+        const c_int *leave, c_int nb_leave, c_float *rowsums_out) {
+  const int n = (int)Q->ncol, m = A ? (int)A->nrow : 0;
+  Engine *e = nullptr; int rc;
+  setenv("QPALM_B200_NEWTON", "sparse", 1);
+  rc = make_engine(&e, n, m, A, Q);
+  unsetenv("QPALM_B200_NEWTON");
+  if (rc) return rc;
+  if (!e->sp) { engine_destroy(e); return 7; }
+  int na = 0;
+  if (m > 0) {
+    std::vector<double> ss((size_t)m);
+    std::vector<c_int> act((size_t)m, 0);
+    for (int i = 0; i < m; i++) { ss[i] = sqrt(sigma[i]); if (active) act[i] = active[i]; na += act[i] != 0; }
+    upload(e, e->sigma, sigma, m); upload(e, e->sqrt_sigma, ss.data(), m);
+    cudaStreamSynchronize(e->stream);
+    up_int(e, e->active, act.data(), m);
+  }
+  std::vector<double> neg((size_t)n);
+  for (int i = 0; i < n; i++) neg[i] = -rhs[i];
+  upload(e, e->dphi, neg.data(), n);
+  QB_CUDA_TRY(cudaMemset(e->info_dev, 0, sizeof(int)));
+  if (rowsums_out) {   // Gershgorin row sums of A_J' Sigma_J A_J in the ORIGINAL ordering (boost_gamma)
+    double ub = 0;
+    rc = step_gershgorin_AtSA(e, &ub);
+    rowsums_out[0] = ub;
+  }
+  rc |= step_newton_refactor(e, m > 0, true, beta, na);
+  if (nb_enter > 0) { up_int(e, e->enter, enter, (int)nb_enter); }
+  if (nb_leave > 0) { up_int(e, e->leave, leave, (int)nb_leave); }
+  if (nb_enter + nb_leave > 0) rc |= step_newton_updown(e, (int)nb_enter, (int)nb_leave);
+  rc |= step_newton_solve(e);
+  rc |= download(e, d, e->d, n);
+  if (L_out && perm_out) rc |= sparse_chol_download(e->sp, e->stream, e->spL, L_out, (long long *)perm_out);
+  int info = 0;
+  QB_CUDA_TRY(cudaMemcpy(&info, e->info_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  engine_destroy(e);
+  return rc ? rc : (info ? 1000 + info : 0);
 }
 
 extern "C" int qpalm_b200_lobpcg(const solver_sparse *Q, const c_float *x0, c_float *lambda_out, c_int *iters_out) {

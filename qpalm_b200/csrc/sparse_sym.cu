@@ -14,7 +14,9 @@
 
 #include <algorithm>
 #include <set>
+#include <tuple>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace qb {
 
@@ -25,13 +27,24 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
   std::vector<std::vector<int>> vadj(adj), eadj(n), elem(n);
   std::vector<char> state(n, 0);            // 0 variable, 1 element, 2 dead (absorbed element)
   std::vector<int> degree(n), mark(n, -1), w(n, 0);
-  std::set<std::pair<int, int>> heap;
-  for (int i = 0; i < n; i++) { degree[i] = (int)vadj[i].size(); heap.insert({degree[i], i}); }
+  // ties: QPALM_B200_MD_TIE = 0 lowest index, 1 most recently updated first (AMD's list heads), 2 least recently updated, 3 hashed
+  const char *tb = getenv("QPALM_B200_MD_TIE");
+  const int tie_mode = tb ? atoi(tb) : 1;
+  std::vector<long long> tkey(n, 0);
+  long long stamp = 0;
+  auto tie = [&](int i) -> long long {
+    if (tie_mode == 1) return -(++stamp);
+    if (tie_mode == 2) return ++stamp;
+    if (tie_mode == 3) return (long long)((unsigned)(i * 2654435761u) >> 4);
+    return 0;
+  };
+  std::set<std::tuple<int, long long, int>> heap;
+  for (int i = 0; i < n; i++) { degree[i] = (int)vadj[i].size(); tkey[i] = tie(i); heap.insert({degree[i], tkey[i], i}); }
   order.clear(); order.reserve(n);
   int wbase = 1;
   std::vector<int> Lp;
   for (int k = 0; k < n; k++) {
-    const int p = heap.begin()->second;
+    const int p = std::get<2>(*heap.begin());
     heap.erase(heap.begin());
     order.push_back(p);
     // ---- form the new element L_p ----
@@ -56,7 +69,7 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
     // ---- prune the adjacency of the members, update their degrees ----
     const int lp = (int)Lp.size();
     for (int i : Lp) {
-      heap.erase({degree[i], i});
+      heap.erase({degree[i], tkey[i], i});
       size_t o = 0;
       for (int v : vadj[i]) if (state[v] == 0 && mark[v] != k) vadj[i][o++] = v;   // drop p, members of L_p, eliminated
       vadj[i].resize(o);
@@ -76,7 +89,8 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
       if (d > n - k - 2) d = n - k - 2;
       if (d < 0) d = 0;
       degree[i] = (int)d;
-      heap.insert({degree[i], i});
+      tkey[i] = tie(i);
+      heap.insert({degree[i], tkey[i], i});
     }
     // an element absorbed above (L_e inside L_p) is referenced by no variable any more: all its variables are in L_p and
     // each of them just dropped it; it simply becomes unreachable
@@ -213,7 +227,7 @@ int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const i
     else if (nsm <= 16) merge = zf < 0.8;
     else if (nsm <= 48) merge = zf < 0.1;
     else merge = zf < 0.05;
-    if (!merge) continue;
+    if (!merge || getenv("QPALM_B200_NO_AMALG")) continue;
     first[p] = first[s]; ncol[p] = (int)nsm; zeros[p] = ztot; alive[s] = 0;
     std::vector<int>().swap(rows[s]);
   }

@@ -193,6 +193,49 @@ def random_qp(n, m, dens_A=0.05, dens_M=0.007, seed=0, nonconvex_shift=0.0, name
     return QP(name or f"random_qp_n{n}_m{m}", Q, A, q, bmin, bmax, 0.0, st)
 
 
+def grid_qp(g, seed=0, box=1.0, diag_shift=0.0, name=None, **settings) -> QP:
+    """C2 stand-in (the Maros-Meszaros files are absent -- SYNTHETIC, structurally similar): variables on a
+    g x g grid, Q = weighted 5-point Laplacian + 0.05 I (lower triangle stored), A = [edge differences (2 g (g-1) rows);
+    cell sums over the 4 corners of every cell ((g-1)^2 rows); identity box rows (g^2)].  Q + A'A is a 9-point stencil, so the
+    Newton system stays sparse (CONT-300 / AUG2DCQP class) and goes through the supernodal factorization."""
+    rng = np.random.default_rng(seed)
+    n = g * g
+    idx = np.arange(n).reshape(g, g)
+    rows, cols, vals = [], [], []
+    r = 0
+    edges = []
+    for (a, b) in ((idx[:, :-1], idx[:, 1:]), (idx[:-1, :], idx[1:, :])):
+        a, b = a.ravel(), b.ravel()
+        k = a.size
+        w = 0.5 + rng.random(k)
+        rows += [np.arange(r, r + k)] * 2
+        cols += [a, b]
+        vals += [w, -w]
+        edges.append((a, b))
+        r += k
+    c00, c01, c10, c11 = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    k = c00.size
+    for cc in (c00, c01, c10, c11):
+        rows.append(np.arange(r, r + k)); cols.append(cc); vals.append(0.25 * (0.5 + rng.random(k)))
+    r += k
+    rows.append(np.arange(r, r + n)); cols.append(np.arange(n)); vals.append(np.ones(n))
+    m = r + n
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(m, n))
+    A.sort_indices()
+    ea = np.concatenate([e[0] for e in edges]); eb = np.concatenate([e[1] for e in edges])
+    w = 0.2 + rng.random(ea.size)
+    Lap = sp.csc_matrix((np.concatenate([-w, -w]), (np.concatenate([ea, eb]), np.concatenate([eb, ea]))), shape=(n, n))
+    Lap = Lap + sp.diags(-np.asarray(Lap.sum(axis=1)).ravel() + 0.05 - diag_shift)   # diag_shift > 0.05: indefinite Q
+    Ql = sp.tril(Lap, format="csc"); Ql.sort_indices()
+    q = 2.0 * rng.standard_normal(n)
+    ne = m - n
+    bmin = np.concatenate([-0.2 * rng.random(ne) - 0.05, -box * (0.2 + rng.random(n))])
+    bmax = np.concatenate([0.2 * rng.random(ne) + 0.05, box * (0.2 + rng.random(n))])
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, verbose=0)
+    st.update(settings)
+    return QP(name or f"grid_qp_g{g}", CSC(n, n, Ql.indptr, Ql.indices, Ql.data, -1), CSC.from_scipy(A), q, bmin, bmax, 0.0, st)
+
+
 def _gram(M: np.ndarray) -> np.ndarray:
     """M M' in fp64; uses the GPU through torch when one is visible (data generation only)."""
     try:
