@@ -109,7 +109,8 @@ struct Engine {
 // Host CSC (int64) -> device.  A: m x n general; Q: n x n, only row >= col entries are read.
 int engine_create(Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
                   const long long *Qp, const long long *Qi, const double *Qx,
-                  const double *q, const double *bmin, const double *bmax, bool need_LQ);
+                  const double *q, const double *bmin, const double *bmax, bool need_LQ,
+                  int newton_override = 0 /* 0: density heuristics (or QPALM_B200_NEWTON), 1: dense factor, 2: supernodal */);
 void engine_destroy(Engine *e);
 
 // ---- setup-time operations ------------------------------------------------------------------------

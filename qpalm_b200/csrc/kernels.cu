@@ -1433,7 +1433,7 @@ static int upload_sparse(SparseDev *S, int rows, int cols, const int *p, const i
 
 int engine_create(Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
                   const long long *Qp, const long long *Qi, const double *Qx,
-                  const double *q, const double *bmin, const double *bmax, bool need_LQ) {
+                  const double *q, const double *bmin, const double *bmax, bool need_LQ, int newton_override) {
   *out = nullptr;
   int ndev = 0;
   QB_CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -1449,7 +1449,8 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   std::vector<int> hA_cp, hA_ci, hA_rp, hA_rj;   // host int32 copies of sparse A for the symbolic analysis
   // ---- A ----
   const char *newton_mode = getenv("QPALM_B200_NEWTON");   // dense | sparse: overrides the density heuristics (tests)
-  const bool force_sparse = newton_mode && !strcmp(newton_mode, "sparse"), force_dense = newton_mode && !strcmp(newton_mode, "dense");
+  const bool force_sparse = newton_override == 2 || (!newton_override && newton_mode && !strcmp(newton_mode, "sparse"));
+  const bool force_dense = newton_override == 1 || (!newton_override && newton_mode && !strcmp(newton_mode, "dense"));
   e->A_dense = !force_sparse && (m > 0) && ((double)nnzA >= 0.25 * (double)m * (double)n);
   e->m_lo = 0; e->m_loc = m; e->m_cap = m;
   if (e->A_dense && shard_world() > 1 && m >= shard_world()) {   // row-sharded dense QP (shard.cu): keep only this rank's rows of A

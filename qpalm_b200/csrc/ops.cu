@@ -24,14 +24,14 @@ struct EmptyCSC {
   explicit EmptyCSC(size_t ncol) : p(ncol + 1, 0), i(1, 0), x(1, 0.0) {}
 };
 // engine from optional A (m x n) and optional Q (n x n); missing pieces are empty
-int make_engine(Engine **e, int n, int m, const solver_sparse *A, const solver_sparse *Q, bool need_LQ = false) {
+int make_engine(Engine **e, int n, int m, const solver_sparse *A, const solver_sparse *Q, bool need_LQ = false, int newton_override = 0) {
   EmptyCSC ea((size_t)n), eq((size_t)n);
   std::vector<double> zn((size_t)n + 1, 0.0), zm((size_t)m + 1, 0.0);
   const long long *Ap = A ? (const long long *)A->p : ea.p.data(), *Ai = A ? (const long long *)A->i : ea.i.data();
   const double *Ax = A ? (const double *)A->x : ea.x.data();
   const long long *Qp = Q ? (const long long *)Q->p : eq.p.data(), *Qi = Q ? (const long long *)Q->i : eq.i.data();
   const double *Qx = Q ? (const double *)Q->x : eq.x.data();
-  return engine_create(e, n, m, Ap, Ai, Ax, Qp, Qi, Qx, zn.data(), zm.data(), zm.data(), need_LQ);
+  return engine_create(e, n, m, Ap, Ai, Ax, Qp, Qi, Qx, zn.data(), zm.data(), zm.data(), need_LQ, newton_override);
 }
 int up_int(Engine *e, int *dst, const c_int *src, int len) {
   std::vector<int> t((size_t)len + 1);
@@ -183,7 +183,7 @@ extern "C" int qpalm_b200_newton_solve(const solver_sparse *Q, const solver_spar
         const c_int *active, c_float beta, const c_float *rhs, c_float *d, c_float *L_out) {
   const int n = (int)Q->ncol, m = A ? (int)A->nrow : 0;
   Engine *e = nullptr; int rc;
-  if ((rc = make_engine(&e, n, m, A, Q))) return rc;
+  if ((rc = make_engine(&e, n, m, A, Q, false, L_out ? 1 : 0))) return rc;   // a dense L can only be returned by the dense path
   int na = 0;
   if (active && m > 0) {
     std::vector<double> ss((size_t)m);
@@ -212,7 +212,7 @@ extern "C" int qpalm_b200_newton_solve(const solver_sparse *Q, const solver_spar
 extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *W, c_int update) {
   const int n = (int)n_, k = (int)k_;
   Engine *e = nullptr; int rc;
-  if ((rc = make_engine(&e, n, 0, nullptr, nullptr))) return rc;
+  if ((rc = make_engine(&e, n, 0, nullptr, nullptr, false, 1))) return rc;   // dense-factor operator: never the supernodal path
   const int ld = e->ld, npad = e->npad;
   std::vector<double> Lp((size_t)ld * npad, 0.0);
   for (int j = 0; j < npad; j++) for (int i = j; i < npad; i++)
