@@ -7,6 +7,8 @@
 //   cholmod_updown                 -> chol_updown  (rank-k recurrence of t_cholmod_updown_numkr.c:289-376
 //                                                   restated for L L' and panelised for the GPU)
 #include "dense.cuh"
+#include <vector>
+#include <stdlib.h>
 
 namespace qb {
 
@@ -170,114 +172,287 @@ int dgemm_nt_batched(cudaStream_t s, int nb, int M, int N, int K, const int *Kz,
 // 128 x 128 diagonal block: Cholesky factor + inverse of the factor, one CTA, all in shared memory.
 // ================================================================================================
 namespace diag {
-// 128 x 128 diagonal block: Cholesky factor + inverse of the factor, one CTA, all in shared memory.
-// Blocked in 32-column sub-panels: a 32 x 32 block is factorised by ONE WARP in registers (row per lane,
-// pivots and multipliers exchanged with shuffles), the rows below are solved against it one row per
-// thread (row in registers, factor entries broadcast from shared memory), then all 512 threads apply the
-// rank-32 trailing update.  The inverse is formed block row by block row from the four 32 x 32 inverses.
-constexpr int NB = 128, DS = 129, NT = 512, SB = 32, RSD = 97;
-constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + NB * (NB + 1) / 2 + SB * RSD + NB) + 16;
+// 128 x 128 diagonal block: Cholesky factor + inverse of the factor, one CTA of 8 warps, everything in shared memory.
+//
+// Right-looking over four 32-column sub-panels.  Per sub-panel kb (rows/cols r0 = 32 kb ..):
+//   S1  warp 0:      factor the 32 x 32 diagonal block in registers (lane = row; template-unrolled so every register
+//                    index is static; one shuffle + one reciprocal + one FMA on the critical path per column), then
+//                    invert it (lane = column of the inverse) into Xb (natural layout) and into the upper triangle
+//                    of As (transposed), whose diagonal carries 1/L(c,c).
+//       warps 1..7:  meanwhile form R = L(block row kb, cols < r0) * X(< r0, < r0) for the inverse of the whole block
+//                    (only needs data that is final before S1) -> hidden under the serial factorization.
+//   S2  all warps:   X(block row kb, cols < r0) = -Xbb * R;  L21 = A21 * Xbb'  (rows below the block) into the
+//                    transposed panel buffer Pt.
+//   S3  all warps:   trailing update A22 -= L21 L21' from Pt (4 x 4 register tiles, 128-bit shared loads) and
+//                    copy of Pt back into As.
+// The inverse X (lower triangular) lives transposed in the upper triangle of As: X(i,c) at As[c*DS + i].
+constexpr int NB = 128, DS = 129, NT = 256, SB = 32, XS = 33, PS = 100;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + SB * XS + (NB - SB) * XS + SB * PS + NB) + 16;
 
-__device__ __forceinline__ int pidx(int i, int c) { return i * (i + 1) / 2 + c; }
+// branch-free 1/sqrt(p): hardware seed (about 22 bits) + two Newton steps; no slow-path call, so the whole
+// 32-column factorization stays one straight-line block the scheduler can interleave
+__device__ __forceinline__ double rsqrt_nr(double p) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double e = fma(-(p * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
 
-__device__ void factor32_warp(double *As, double *rdiag, int base, int lane, int *info, int col0) {
+template <int J>
+__device__ __forceinline__ void fstep(double (&a)[SB], const int lane, double &dl, double &dinv, int &badcol) {
+  const double pjj = __shfl_sync(FULL, a[J], J);
+  const double y = rsqrt_nr(pjj);          // 1 / L(J,J)
+  const double s = a[J] * (y * y);         // a[J] / pjj
+#pragma unroll
+  for (int c = J + 1; c < SB; c++) {
+    const double lcj = __shfl_sync(FULL, a[J], c);
+    a[c] = fma(-s, lcj, a[c]);
+  }
+  double ljj = pjj * y;
+  ljj = fma(fma(-ljj, ljj, pjj), 0.5 * y, ljj);
+  if (!(pjj > 0.0) && badcol < 0) badcol = J;
+  a[J] *= y;
+  if (lane == J) { dl = ljj; dinv = y; }
+  if constexpr (J + 1 < SB) fstep<J + 1>(a, lane, dl, dinv, badcol);
+}
+
+// one warp: in-register Cholesky of the 32 x 32 block at (base, base); strictly-lower part of L back into As,
+// 1/L(j,j) onto the diagonal of As, L(j,j) into ldiag.
+__device__ __forceinline__ void factor32_warp(double *As, double *ldiag, int base, int lane, int *info, int col0) {
   double a[SB];
 #pragma unroll
   for (int c = 0; c < SB; c++) a[c] = (c <= lane) ? As[(base + lane) * DS + base + c] : 0.0;
-  bool bad = false;
+  double dl = 0.0, dinv = 0.0;
+  int badcol = -1;
+  fstep<0>(a, lane, dl, dinv, badcol);
+  if (badcol >= 0 && lane == 0 && info) atomicCAS(info, 0, col0 + base + badcol + 1);
 #pragma unroll
-  for (int j = 0; j < SB; j++) {
-    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(pjj > 0.0) && !bad) { bad = true; if (lane == 0 && info) atomicCAS(info, 0, col0 + base + j + 1); }
-    const double ljj = sqrt(pjj), inv = 1.0 / ljj;
-    if (lane == j) { a[j] = ljj; rdiag[base + j] = inv; }
-    else if (lane > j) a[j] *= inv;
-    // constant inner bounds + predicate (a j-dependent bound is unrolled before the outer loop and leaves a[] in
-    // local memory); the dead half folds away after the outer unroll
-#pragma unroll
-    for (int c = 0; c < SB; c++) {
-      if (c > j) {
-        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-        if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < SB; c++) if (c <= lane) As[(base + lane) * DS + base + c] = a[c];
+  for (int c = 0; c < SB; c++) if (c < lane) As[(base + lane) * DS + base + c] = a[c];
+  As[(base + lane) * DS + base + lane] = dinv;
+  ldiag[base + lane] = dl;
 }
 
-// rows i > base+31: A(i, base..base+31) <- A(i, ..) * inv(L_bb)'  by forward substitution, one row per thread
-__device__ void panel_solve(double *As, const double *rdiag, int base, int tid) {
-  const int i = base + SB + tid;
-  if (i >= NB) return;
+// right-looking column sweep of X = inv(L_bb), lane = column of X: v[r] accumulates sum_t L(r,t) x(t) until row r
+// is finalised; 31 - R independent FMAs per step, no lane-dependent branches
+template <int R>
+__device__ __forceinline__ void istep(const double *Lb, double (&v)[SB], const int lane) {
+  const double rd = Lb[R * DS + R];         // 1 / L(R,R)
+  double xr = (R == lane) ? rd : -v[R] * rd;
+  xr = (R < lane) ? 0.0 : xr;
+  v[R] = xr;
+#pragma unroll
+  for (int q = R + 1; q < SB; q++) v[q] = fma(Lb[q * DS + R], xr, v[q]);
+  if constexpr (R + 1 < SB) istep<R + 1>(Lb, v, lane);
+}
+
+// one warp: Xbb = inv(L_bb).  Natural layout into Xb (zeros above the diagonal), transposed into the upper
+// triangle of the As block.
+__device__ __forceinline__ void inv32_warp(double *As, double *Xb, int base, int lane) {
   double v[SB];
 #pragma unroll
-  for (int c = 0; c < SB; c++) v[c] = As[i * DS + base + c];
-#pragma unroll
-  for (int c = 0; c < SB; c++) {
-    double s = v[c];
-#pragma unroll
-    for (int t = 0; t < SB; t++) if (t < c) s = fma(-v[t], As[(base + c) * DS + base + t], s);
-    v[c] = s * rdiag[base + c];
-  }
-#pragma unroll
-  for (int c = 0; c < SB; c++) As[i * DS + base + c] = v[c];
-}
-
-// A(i,k) -= sum_t L(i, base+t) L(k, base+t) for base+32 <= k <= i < 128
-__device__ void trailing_update(double *As, int base, int tid) {
-  const int tx = tid & 31, ty = tid >> 5, start = base + SB;
-  for (int i = start + ty; i < NB; i += NT / 32) {
-    const double *Li = As + i * DS + base;
-    for (int k = start + tx; k <= i; k += 32) {
-      const double *Lk = As + k * DS + base;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int t = 0; t < SB; t += 2) { s0 = fma(Li[t], Lk[t], s0); s1 = fma(Li[t + 1], Lk[t + 1], s1); }
-      As[i * DS + k] -= (s0 + s1);
-    }
-  }
-}
-
-// X_bb = inv(L_bb) for the 32 x 32 diagonal block at `base`; lane = column of X
-__device__ void inv32_warp(const double *As, double *Xs, const double *rdiag, int base, int lane) {
-  double x[SB];
+  for (int r = 0; r < SB; r++) v[r] = 0.0;
+  istep<0>(As + base * DS + base, v, lane);
 #pragma unroll
   for (int r = 0; r < SB; r++) {
-    double s = 0.0;
-#pragma unroll
-    for (int t = 0; t < SB; t++) if (t < r) s = fma(As[(base + r) * DS + base + t], x[t], s);   // x[t] == 0 for t < lane
-    x[r] = (r < lane) ? 0.0 : ((r == lane) ? rdiag[base + r] : -s * rdiag[base + r]);
+    Xb[r * XS + lane] = v[r];
+    if (r > lane) As[(base + lane) * DS + base + r] = v[r];
   }
-#pragma unroll
-  for (int r = 0; r < SB; r++) if (r >= lane) Xs[pidx(base + r, base + lane)] = x[r];
 }
 
-__device__ void inverse_from_factor(const double *As, double *Xs, double *Rs, const double *rdiag, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-  if (warp < 4) inv32_warp(As, Xs, rdiag, warp * SB, lane);
-  __syncthreads();
+// acc[a][b] += sum_{u0 <= u < u1} P[a*ps + u] * Q[b*qs + u]
+template <int TR, int TC>
+__device__ __forceinline__ void dot_tile(const double *P, int ps, const double *Q, int qs, int u0, int u1,
+                                         double (&acc)[TR][TC]) {
+#pragma unroll 4
+  for (int u = u0; u < u1; u++) {
+    double p[TR], q[TC];
 #pragma unroll
-  for (int bi = 1; bi < 4; bi++) {
-    const int width = SB * bi, r0 = SB * bi;
-    // R = - L(block row bi, cols < r0) * X(rows < r0, cols < r0)
-    for (int idx = tid; idx < SB * width; idx += NT) {
-      const int r = idx / width, c = idx - r * width;
-      const double *Lr = As + (r0 + r) * DS;
-      double s = 0.0;
-      for (int u = c; u < r0; u++) s = fma(Lr[u], Xs[pidx(u, c)], s);
-      Rs[r * RSD + c] = -s;
+    for (int a = 0; a < TR; a++) p[a] = P[a * ps + u];
+#pragma unroll
+    for (int b = 0; b < TC; b++) q[b] = Q[b * qs + u];
+#pragma unroll
+    for (int a = 0; a < TR; a++)
+#pragma unroll
+      for (int b = 0; b < TC; b++) acc[a][b] = fma(p[a], q[b], acc[a][b]);
+  }
+}
+
+// Thread tiles are 2 rows x 4 columns with the two rows half a panel apart and the lanes of a warp running along the
+// rows: row operands (stride DS or XS, both odd) then fall into distinct banks and the column operand is a broadcast.
+
+// Rt(c, r) = sum_{u = c}^{r0 - 1} L(r0 + r, u) X(u, c),  r < 32, c < r0
+__device__ __forceinline__ void inv_offdiag_R(const double *As, double *Rt, int r0, int t, int nthr) {
+  const int ntiles = 16 * (r0 >> 2);
+  for (int tile = t; tile < ntiles; tile += nthr) {
+    const int tr = tile & 15, c0 = 4 * (tile >> 4);
+    double acc[2][4] = {};
+    const double *P = As + (r0 + tr) * DS, *Q = As + c0 * DS;
+    // triangular head: X(u, c0 + b) exists for u >= c0 + b (the diagonal of As holds X(c,c))
+#pragma unroll
+    for (int uu = 0; uu < 4; uu++) {
+      const int u = c0 + uu;
+      const double p0 = P[u], p1 = P[16 * DS + u];
+#pragma unroll
+      for (int b = 0; b <= uu; b++) {
+        const double q = Q[b * DS + u];
+        acc[0][b] = fma(p0, q, acc[0][b]);
+        acc[1][b] = fma(p1, q, acc[1][b]);
+      }
     }
-    __syncthreads();
-    // X(block row bi, cols < r0) = X_bb * R
-    for (int idx = tid; idx < SB * width; idx += NT) {
-      const int r = idx / width, c = idx - r * width;
-      double s = 0.0;
-      for (int u = 0; u <= r; u++) s = fma(Xs[pidx(r0 + r, r0 + u)], Rs[u * RSD + c], s);
-      Xs[pidx(r0 + r, c)] = s;
+    dot_tile<2, 4>(P, 16 * DS, Q, DS, c0 + 4, r0, acc);
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) Rt[(c0 + b) * XS + tr + 16 * a] = acc[a][b];
+  }
+}
+
+// X(r0 + r, c) = - sum_{u <= r} Xbb(r, u) Rt(c, u), stored transposed at As[c*DS + r0 + r]
+__device__ __forceinline__ void inv_offdiag_X(double *As, const double *Xb, const double *Rt, int r0, int t, int nthr) {
+  const int ntiles = 16 * (r0 >> 2);
+  for (int tile = t; tile < ntiles; tile += nthr) {
+    const int tr = tile & 15, c0 = 4 * (tile >> 4);
+    double acc[2][4] = {};
+    dot_tile<2, 4>(Xb + tr * XS, 16 * XS, Rt + c0 * XS, XS, 0, tr + 17, acc);   // Xb is zero above its diagonal
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) As[(c0 + b) * DS + r0 + tr + 16 * a] = -acc[a][b];
+  }
+}
+
+// position of panel row i (relative to the first trailing row) inside one Pt column: rows 4t, 4t+1 of all 4-row groups
+// first, rows 4t+2, 4t+3 after them, so that the 128-bit loads of consecutive groups are consecutive
+__device__ __forceinline__ int pt_pos(int i) { return ((i >> 1) & 1) * 48 + ((i >> 2) << 1) + (i & 1); }
+
+// Pt(c, i - r1) = sum_{u <= c} A(i, base + u) Xbb(c, u) for rows i >= r1 = base + 32 (the new L21, transposed)
+__device__ __forceinline__ void panel_solve(const double *As, const double *Xb, double *Pt, int base, int t, int nthr) {
+  const int r1 = base + SB, half = (NB - r1) >> 1, ntiles = half * 8;
+  for (int tile = t; tile < ntiles; tile += nthr) {
+    const int tc = tile / half, tr = tile - tc * half, c0 = 4 * tc;
+    double acc[2][4] = {};
+    dot_tile<2, 4>(As + (r1 + tr) * DS + base, half * DS, Xb + c0 * XS, XS, 0, c0 + 4, acc);
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) Pt[(c0 + b) * PS + pt_pos(tr + a * half)] = acc[a][b];
+  }
+}
+
+// A(i, k) -= sum_u Pt(u, i - r1) Pt(u, k - r1) for r1 <= k <= i < 128, and L21 copied from Pt into As
+__device__ __forceinline__ void trailing_update(double *As, const double *Pt, int base, int t, int nthr) {
+  const int r1 = base + SB, nrow = NB - r1, nt = nrow >> 2, ntiles = nt * (nt + 1) / 2;
+  for (int tile = t; tile < ntiles; tile += nthr) {
+    int ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > tile) ti--;
+    while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+    const int tk = tile - ti * (ti + 1) / 2;
+    double acc[4][4] = {};
+#pragma unroll 4
+    for (int u = 0; u < SB; u++) {
+      const double2 pa = *reinterpret_cast<const double2 *>(Pt + u * PS + 2 * ti);
+      const double2 pb = *reinterpret_cast<const double2 *>(Pt + u * PS + 48 + 2 * ti);
+      const double2 qa = *reinterpret_cast<const double2 *>(Pt + u * PS + 2 * tk);
+      const double2 qb = *reinterpret_cast<const double2 *>(Pt + u * PS + 48 + 2 * tk);
+      const double p[4] = {pa.x, pa.y, pb.x, pb.y}, q[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = fma(p[a], q[b], acc[a][b]);
     }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int i = r1 + 4 * ti + a, k = r1 + 4 * tk + b;
+        if (k <= i) As[i * DS + k] -= acc[a][b];
+      }
+  }
+  for (int idx = t; idx < nrow * SB; idx += nthr) {
+    const int u = idx / nrow, i = idx - u * nrow;
+    As[(r1 + i) * DS + base + u] = Pt[u * PS + pt_pos(i)];
+  }
+}
+
+template <bool PROF>
+__device__ __forceinline__ void diag_body(double *Lg, int ld, double *Xg, int *info, int col0, int factor, int block_stride,
+                                          long long strideL, long long strideX, const int *mask, long long *clk) {
+  if (mask && !mask[blockIdx.y]) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *As = reinterpret_cast<double *>(smem_raw);
+  double *Pt = As + NB * DS;              // 16-byte aligned (NB*DS is even)
+  double *Xb = Pt + SB * PS;
+  double *Rt = Xb + SB * XS;
+  double *ldiag = Rt + (NB - SB) * XS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int nclk = 0;
+#define DIAG_TICK() do { if (PROF && tid == 0) clk[nclk++] = clock64(); } while (0)
+  Lg += (size_t)blockIdx.y * strideL + (size_t)blockIdx.x * block_stride * (size_t)(ld + 1);
+  Xg += (size_t)blockIdx.y * strideX + (size_t)blockIdx.x * NB * NB;
+  if (info) info += blockIdx.y;
+  col0 += blockIdx.x * block_stride;
+  DIAG_TICK();
+#pragma unroll 1
+  for (int it = 0; it < NB * NB / NT; it += 16) {     // 16 independent loads in flight per thread
+    double t[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + (it + q) * NT, i = idx & (NB - 1), k = idx >> 7;
+      t[q] = (k <= i) ? Lg[i + (size_t)ld * k] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + (it + q) * NT, i = idx & (NB - 1), k = idx >> 7;
+      if (k <= i) As[i * DS + k] = t[q];
+    }
+  }
+  __syncthreads();
+  if (!factor) {
+    if (tid < NB) { const double d = As[tid * DS + tid]; ldiag[tid] = d; As[tid * DS + tid] = 1.0 / d; }
     __syncthreads();
   }
+  DIAG_TICK();
+#pragma unroll 1
+  for (int kb = 0; kb < 4; kb++) {
+    const int base = kb * SB;
+    if (warp == 0) {
+      if (factor) { factor32_warp(As, ldiag, base, lane, info, col0); __syncwarp(); }
+      DIAG_TICK();
+      inv32_warp(As, Xb, base, lane);
+      DIAG_TICK();
+    } else if (kb > 0 && warp != 4) {
+      // warp 4 shares warp 0's SM sub-partition (issue port, FP64 unit): keep it idle while warp 0 runs the serial chain
+      inv_offdiag_R(As, Rt, base, tid - 32 - (warp > 4 ? 32 : 0), NT - 64);
+    }
+    __syncthreads();
+    DIAG_TICK();
+    if (kb > 0) inv_offdiag_X(As, Xb, Rt, base, tid, NT);
+    if (factor && kb < 3) {
+      panel_solve(As, Xb, Pt, base, tid, NT);
+      __syncthreads();
+      DIAG_TICK();
+      trailing_update(As, Pt, base, tid, NT);
+    }
+    __syncthreads();
+    DIAG_TICK();
+  }
+  if (factor) {
+    for (int idx = tid; idx < NB * NB; idx += NT) {
+      const int i = idx & (NB - 1), k = idx >> 7;
+      if (k <= i) Lg[i + (size_t)ld * k] = (k == i) ? ldiag[i] : As[i * DS + k];
+    }
+  }
+  for (int idx = tid; idx < NB * NB; idx += NT) {
+    const int i = idx & (NB - 1), c = idx >> 7;
+    Xg[i + (size_t)NB * c] = (c <= i) ? As[c * DS + i] : 0.0;
+  }
+  DIAG_TICK();
+#undef DIAG_TICK
 }
 
 // factor == 1: the block (lower) is factorised in place, then inverted.  factor == 0: the block already
@@ -286,48 +461,12 @@ __device__ void inverse_from_factor(const double *As, double *Xs, double *Rs, co
 __global__ void __launch_bounds__(NT, 1)
 k_diag_block(double *Lg, int ld, double *Xg, int *info, int col0, int factor, int block_stride,
              long long strideL, long long strideX, const int *mask) {
-  if (mask && !mask[blockIdx.y]) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *As = reinterpret_cast<double *>(smem_raw);
-  double *Xs = As + NB * DS;
-  double *Rs = Xs + NB * (NB + 1) / 2;
-  double *rdiag = Rs + SB * RSD;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Lg += (size_t)blockIdx.y * strideL + (size_t)blockIdx.x * block_stride * (size_t)(ld + 1);
-  Xg += (size_t)blockIdx.y * strideX + (size_t)blockIdx.x * NB * NB;
-  if (info) info += blockIdx.y;
-  col0 += blockIdx.x * block_stride;
-  for (int idx = tid; idx < NB * NB; idx += NT) {
-    const int i = idx & (NB - 1), k = idx >> 7;
-    if (k <= i) As[i * DS + k] = Lg[i + (size_t)ld * k];
-  }
-  __syncthreads();
-  if (factor) {
-#pragma unroll 1
-    for (int kb = 0; kb < 4; kb++) {
-      const int base = kb * SB;
-      if (warp == 0) factor32_warp(As, rdiag, base, lane, info, col0);
-      __syncthreads();
-      if (kb < 3) {
-        panel_solve(As, rdiag, base, tid);
-        __syncthreads();
-        trailing_update(As, base, tid);
-        __syncthreads();
-      }
-    }
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-      const int i = idx & (NB - 1), k = idx >> 7;
-      if (k <= i) Lg[i + (size_t)ld * k] = As[i * DS + k];
-    }
-  } else {
-    if (tid < NB) rdiag[tid] = 1.0 / As[tid * DS + tid];
-    __syncthreads();
-  }
-  inverse_from_factor(As, Xs, Rs, rdiag, tid);
-  for (int idx = tid; idx < NB * NB; idx += NT) {
-    const int i = idx & (NB - 1), c = idx >> 7;
-    Xg[i + (size_t)NB * c] = (c <= i) ? Xs[pidx(i, c)] : 0.0;
-  }
+  diag_body<false>(Lg, ld, Xg, info, col0, factor, block_stride, strideL, strideX, mask, nullptr);
+}
+// instrumented twin (tools/microbench.py): thread 0 records clock64() at every phase boundary
+__global__ void __launch_bounds__(NT, 1)
+k_diag_block_prof(double *Lg, int ld, double *Xg, int factor, long long *clk) {
+  diag_body<true>(Lg, ld, Xg, nullptr, 0, factor, 0, 0, 0, nullptr, clk);
 }
 }  // namespace diag
 
@@ -338,6 +477,27 @@ static int diag_attr() {
                                      (int)diag::kSmemBytes));
     set = true;
   }
+  return 0;
+}
+
+// phase clocks of one 128 x 128 factor+inverse (out: up to 32 clock64 samples, returns the count)
+int diag_block_phase_clocks(long long *out32) {
+  QB_CUDA_TRY(cudaFuncSetAttribute(diag::k_diag_block_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag::kSmemBytes));
+  const int n = diag::NB;
+  std::vector<double> A((size_t)n * n);
+  for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) A[i + (size_t)n * j] = (i == j) ? n + 1.0 : 1.0 / (1.0 + abs(i - j));
+  double *dA = nullptr, *dX = nullptr; long long *dc = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&dA, sizeof(double) * n * n));
+  QB_CUDA_TRY(cudaMalloc(&dX, sizeof(double) * n * n));
+  QB_CUDA_TRY(cudaMalloc(&dc, sizeof(long long) * 32));
+  for (int rep = 0; rep < 2; rep++) {
+    QB_CUDA_TRY(cudaMemcpy(dA, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    QB_CUDA_TRY(cudaMemset(dc, 0, sizeof(long long) * 32));
+    diag::k_diag_block_prof<<<1, diag::NT, diag::kSmemBytes>>>(dA, n, dX, 1, dc);
+    QB_CUDA_TRY(cudaDeviceSynchronize());
+  }
+  QB_CUDA_TRY(cudaMemcpy(out32, dc, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dX); cudaFree(dc);
   return 0;
 }
 

@@ -213,3 +213,7 @@ extern "C" int qpalm_b200_microbench_diag(long long *out2) {
   cudaFree(c); cudaFree(d);
   return 0;
 }
+
+// phase clocks of the 128 x 128 diagonal-block kernel (dense.cu); out32: clock64 samples at the phase boundaries
+namespace qb { int diag_block_phase_clocks(long long *out32); }
+extern "C" int qpalm_b200_microbench_diag_phases(long long *out32) { return qb::diag_block_phase_clocks(out32); }

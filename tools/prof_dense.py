@@ -18,3 +18,15 @@ elif what == "syrk":
     lib.qpalm_b200_bench_dsyrk.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double)]
     rc = lib.qpalm_b200_bench_dsyrk(n, k, 2, C.byref(ms))
     print("syrk", n, k, "ms", ms.value, "TFLOP/s", n * n * k / ms.value / 1e9)
+elif what == "potrf_prof":
+    # per-kernel CUDA-event breakdown of one blocked Cholesky
+    lib.qpalm_b200_bench_potrf.argtypes = [abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    lib.qpalm_b200_bench_potrf(n, 1, C.byref(ms))
+    lib.qpalm_b200_prof_enable(b"*")
+    lib.qpalm_b200_bench_potrf(n, 0, C.byref(ms))
+    buf = C.create_string_buffer(1 << 16)
+    lib.qpalm_b200_prof_report(buf, len(buf))
+    import json
+    rep = json.loads(buf.value.decode())
+    for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+        print(f"  {k:28s} launches {v['launches']:6d}  ms {v['ms']:9.3f}  mean_us {1e3 * v['ms'] / v['launches']:8.2f}")
