@@ -306,6 +306,21 @@ int  qpalm_b200_shard_init(int rank, int world, const char *id128);
 void qpalm_b200_shard_finalize(void);
 
 /* ------------------------------------------------------------------------------------------------
+ * Part 2c -- QPS front end: replaces interfaces/qps/src/qpalm_qps.c.
+ * qps_read  = get_sizes_and_check_format + read_data (qpalm_qps.c:69-575): the returned QPALMData holds A with the
+ *             reference's appended bound rows (one per column without an FR bound, below the constraint rows),
+ *             Q as the QUADOBJ lower triangle (stype -1), q, c = -RHS(objective), bmin/bmax.  Free with qps_free.
+ *             Returns 0 ok, 1 cannot open, 2 format error.
+ * read_settings = read_settings (qpalm_qps.c:610-689): defaults, then "name value" pairs after five header lines.
+ * qps_solve = main (qpalm_qps.c:692-831): read, qpalm_setup (device upload), qpalm_solve, copy the solution out.
+ * ---------------------------------------------------------------------------------------------- */
+int  qpalm_b200_qps_read(const char *path, QPALMData **data_out, char *name_out, size_t name_len);
+void qpalm_b200_qps_free(QPALMData *data);
+int  qpalm_b200_read_settings(const char *path, QPALMSettings *settings);
+int  qpalm_b200_qps_solve(const char *qps_path, const char *settings_path, QPALMInfo *info_out,
+                          c_float *x_out, c_float *y_out, size_t *n_io, size_t *m_io);
+
+/* ------------------------------------------------------------------------------------------------
  * Part 3 -- batch entry point (additive).  `nb` QPs sharing Q, A (values and pattern) and settings
  * but with their own q, bmin, bmax.  Each instance's result equals what qpalm_setup + qpalm_solve
  * return for that instance alone.  q: nb x n, bmin/bmax: nb x m (row-major, one instance per row).
