@@ -190,34 +190,42 @@ constexpr int NB = 128, DS = 129, NT = 256, SB = 32, XS = 33, PS = 100;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + SB * XS + (NB - SB) * XS + SB * PS + NB) + 16;
 
-// branch-free 1/sqrt(p): hardware seed (about 22 bits) + two Newton steps; no slow-path call, so the whole
-// 32-column factorization stays one straight-line block the scheduler can interleave
-__device__ __forceinline__ double rsqrt_nr(double p) {
+// Branch-free sqrt(p) and 1/sqrt(p) for a normal positive p: hardware 1/sqrt seed (about 22 bits), two coupled Newton
+// steps on (g, h) ~ (sqrt p, 1/(2 sqrt p)), Markstein's final correction for g (correctly rounded sqrt), then the
+// reciprocal of g from the seed 2h with two FMA corrections.  Same values as sqrt() and 1.0 / sqrt() of the reference
+// arithmetic for normal inputs, but without their slow-path calls, so the 32-column factorization stays one straight-line
+// block the scheduler can interleave.  A non-positive p gives NaN (flagged by the caller).
+__device__ __forceinline__ void sqrt_and_rcp(double p, double &g, double &x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  g = p * y;
+  double h = 0.5 * y;
 #pragma unroll
   for (int it = 0; it < 2; it++) {
-    const double e = fma(-(p * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
   }
-  return y;
+  g = fma(fma(-g, g, p), h, g);
+  x = h + h;
+#pragma unroll
+  for (int it = 0; it < 2; it++) x = fma(x, fma(-g, x, 1.0), x);
 }
 
 template <int J>
 __device__ __forceinline__ void fstep(double (&a)[SB], const int lane, double &dl, double &dinv, int &badcol) {
   const double pjj = __shfl_sync(FULL, a[J], J);
-  const double y = rsqrt_nr(pjj);          // 1 / L(J,J)
-  const double s = a[J] * (y * y);         // a[J] / pjj
+  double ljj, inv;
+  sqrt_and_rcp(pjj, ljj, inv);
+  const double lij = a[J] * inv;           // L(row, J)
 #pragma unroll
   for (int c = J + 1; c < SB; c++) {
-    const double lcj = __shfl_sync(FULL, a[J], c);
-    a[c] = fma(-s, lcj, a[c]);
+    const double lcj = __shfl_sync(FULL, a[J], c) * inv;   // L(c, J), the value lane c itself stores
+    a[c] = fma(-lij, lcj, a[c]);
   }
-  double ljj = pjj * y;
-  ljj = fma(fma(-ljj, ljj, pjj), 0.5 * y, ljj);
   if (!(pjj > 0.0) && badcol < 0) badcol = J;
-  a[J] *= y;
-  if (lane == J) { dl = ljj; dinv = y; }
+  a[J] = lij;
+  if (lane == J) { dl = ljj; dinv = inv; }
   if constexpr (J + 1 < SB) fstep<J + 1>(a, lane, dl, dinv, badcol);
 }
 
@@ -508,25 +516,63 @@ int diag_block_phase_clocks(long long *out32) {
 // four times better than rank-128 updates.
 constexpr int kOuter = 512;
 
+// Look-ahead (single matrix, npad > 2 * kOuter): the panel chain of an outer block (diagonal-block kernel on one SM,
+// panel solves on npad/128 SMs at most) is latency-bound and leaves most of the GPU idle, while the rank-512 update of
+// everything to the right is throughput-bound.  The update is therefore split: the part that lands on the NEXT outer
+// block's columns is applied first, and the panel chain of that block then runs on a high-priority stream while the
+// rest of the update fills the remaining SMs from the caller's stream.  CTAs of the high-priority stream are placed
+// as soon as any SM frees up (an update CTA lasts < 100 us), so the chain is not starved by the queued update.
+namespace {
+struct LookAhead {
+  cudaStream_t hi = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_chain = nullptr, ev_rest = nullptr;
+  int device = -1;
+  int init() {
+    int dev = 0;
+    QB_CUDA_TRY(cudaGetDevice(&dev));
+    if (hi && dev == device) return 0;
+    int lo_p = 0, hi_p = 0;
+    QB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    QB_CUDA_TRY(cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hi_p));
+    QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
+    QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
+    device = dev;
+    return 0;
+  }
+};
+thread_local LookAhead g_la;
+}  // namespace
+
 int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, long long sL, double *invdiag, long long sX,
                         int *info_dev, const int *mask) {
   if (int e = diag_attr()) return e;
+  static const bool la_env_off = getenv("QPALM_B200_NO_LOOKAHEAD") != nullptr;
+  const bool la = (nb == 1 && !mask && npad > 2 * kOuter && !la_env_off);
+  cudaStream_t sc = s;          // stream of the panel chain
+  bool rest_pending = false;    // a "rest" update is in flight on s
+  if (la) {
+    if (int e = g_la.init()) return e;
+    sc = g_la.hi;
+    QB_CUDA_TRY(cudaEventRecord(g_la.ev_in, s));
+    QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_in, 0));
+  }
   for (int J0 = 0; J0 < npad; J0 += kOuter) {
     const int Jend = (J0 + kOuter < npad) ? J0 + kOuter : npad;
     for (int j0 = J0; j0 < Jend; j0 += kPanel) {
       double *Ljj = L + j0 + (size_t)j0 * ld;
       double *Xp = invdiag + (size_t)(j0 / kPanel) * kPanel * kPanel;
-      QB_LAUNCH(diag::k_diag_block, dim3(1, nb), diag::NT, diag::kSmemBytes, s, Ljj, ld, Xp, info_dev, j0, 1, 0, sL, sX, mask);
+      QB_LAUNCH(diag::k_diag_block, dim3(1, nb), diag::NT, diag::kSmemBytes, sc, Ljj, ld, Xp, info_dev, j0, 1, 0, sL, sX, mask);
       const int rem = npad - j0 - kPanel;
       if (rem <= 0) continue;
       double *L21 = Ljj + kPanel;
       // L21 <- A21 * inv(L11)'   (in place, one 128-wide tile column)
-      if (int e = dgemm_nt_batched(s, nb, rem, kPanel, kPanel, nullptr, L21, ld, sL, Xp, kPanel, sX, L21, ld, sL, 1.0, 0.0, false, mask)) return e;
+      if (int e = dgemm_nt_batched(sc, nb, rem, kPanel, kPanel, nullptr, L21, ld, sL, Xp, kPanel, sX, L21, ld, sL, 1.0, 0.0, false, mask)) return e;
       // rank-128 update of the remaining columns of THIS outer block (all rows below)
       const int wcols = Jend - (j0 + kPanel);
       if (wcols > 0) {
         double *Cin = L + (j0 + kPanel) + (size_t)(j0 + kPanel) * ld;
-        if (int e = dgemm_nt_batched(s, nb, rem, wcols, kPanel, nullptr, L21, ld, sL, L21, ld, sL, Cin, ld, sL, -1.0, 1.0, true, mask)) return e;
+        if (int e = dgemm_nt_batched(sc, nb, rem, wcols, kPanel, nullptr, L21, ld, sL, L21, ld, sL, Cin, ld, sL, -1.0, 1.0, true, mask)) return e;
       }
     }
     // rank-(Jend-J0) update of everything to the right of the outer block
@@ -534,8 +580,28 @@ int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, lon
     if (rem > 0) {
       const double *P = L + Jend + (size_t)J0 * ld;
       double *A22 = L + Jend + (size_t)Jend * ld;
-      if (int e = dgemm_nt_batched(s, nb, rem, rem, Jend - J0, nullptr, P, ld, sL, P, ld, sL, A22, ld, sL, -1.0, 1.0, true, mask)) return e;
+      const int K = Jend - J0;
+      if (la && rem > kOuter) {
+        // (a) next outer block's columns, on the chain stream -- after the previous "rest" update, which also wrote them
+        if (rest_pending) QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_rest, 0));
+        if (int e = dgemm_nt_batched(sc, 1, rem, kOuter, K, nullptr, P, ld, 0, P, ld, 0, A22, ld, 0, -1.0, 1.0, true, nullptr)) return e;
+        QB_CUDA_TRY(cudaEventRecord(g_la.ev_chain, sc));
+        // (b) the rest, on the caller's stream, concurrent with the next block's panel chain
+        QB_CUDA_TRY(cudaStreamWaitEvent(s, g_la.ev_chain, 0));
+        const double *P2 = P + kOuter;
+        double *A33 = A22 + (size_t)kOuter * (ld + 1);
+        if (int e = dgemm_nt_batched(s, 1, rem - kOuter, rem - kOuter, K, nullptr, P2, ld, 0, P2, ld, 0, A33, ld, 0, -1.0, 1.0, true, nullptr)) return e;
+        QB_CUDA_TRY(cudaEventRecord(g_la.ev_rest, s));
+        rest_pending = true;
+      } else {
+        if (rest_pending) { QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_rest, 0)); rest_pending = false; }
+        if (int e = dgemm_nt_batched(sc, nb, rem, rem, K, nullptr, P, ld, sL, P, ld, sL, A22, ld, sL, -1.0, 1.0, true, mask)) return e;
+      }
     }
+  }
+  if (la) {
+    QB_CUDA_TRY(cudaEventRecord(g_la.ev_chain, sc));
+    QB_CUDA_TRY(cudaStreamWaitEvent(s, g_la.ev_chain, 0));
   }
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
