@@ -22,7 +22,7 @@ c_int_p = C.POINTER(c_int)
 c_float_p = C.POINTER(c_float)
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(REPO_ROOT, "qpalm_b200", "libqpalm_b200.so")
+PRODUCT_LIB = os.environ.get("QPALM_B200_LIB") or os.path.join(REPO_ROOT, "qpalm_b200", "libqpalm_b200.so")   # override: A/B builds
 REF_LIB = os.path.join(REPO_ROOT, "oracle", "_ref", "libqpalm_ref.so")
 ORACLE_LIB = os.path.join(REPO_ROOT, "oracle", "liboracle.so")
 

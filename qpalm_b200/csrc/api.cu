@@ -394,7 +394,7 @@ static bool prefer_updown(const Engine *e, int k) {
   // cost a fraction of a millisecond: follow the reference's own choice (rank update) so that tiny ill-conditioned
   // problems (tests/src/test_dua_inf_qp.c) round alike.
   if (e->npad <= 128) return true;
-  const double t_ud = (e->npad / 32.0) * (0.030 + 0.012 * k);                                   // ms, B200
+  const double t_ud = (e->npad / 32.0) * (0.060 + 0.008 * k);                                   // ms, B200 (measured 83 us per 32-column panel step at n = 8000)
   const double t_rf = (e->npad / 128.0) * 0.12 + ((double)e->n * e->n * e->n / 3.0) / 25e9;      // ms: panel chain + DMMA flops
   return t_ud < t_rf;
 }

@@ -27,13 +27,26 @@ using namespace qb;
 namespace qb {
 namespace bp {
 
-constexpr int NT = 256, NW = NT / 32;
-constexpr int PW = 32;            // panel width
+// Build-time shape of a CTA.  Default: 8 warps, 32-column panel, both sort buffers in shared memory = 80 registers x 256
+// threads, 72 KB -> 3 CTAs / SM.  The 4-CTA shape (-DQB_BP_NT=192 -DQB_BP_PW=24 -DQB_BP_SORT_GLOBAL=1: 55 KB) was measured
+// in round 1: it holds the whole 512-instance sweep in one wave but the two extra panels per factorization and the
+// smaller CTAs cost as much as the second wave saves (138.6 ms either way), so it is not the default.
+#ifndef QB_BP_NT
+#define QB_BP_NT 256
+#endif
+#ifndef QB_BP_PW
+#define QB_BP_PW 32
+#endif
+#ifndef QB_BP_SORT_GLOBAL
+#define QB_BP_SORT_GLOBAL 0
+#endif
+constexpr int NT = QB_BP_NT, NW = NT / 32;
+constexpr int PW = QB_BP_PW;      // panel width (sub-panels of 16 + 8 columns)
 constexpr int NMAX = 240;         // largest n of this engine (panel = PW x LDP doubles of shared memory)
 constexpr int LDP = NMAX + 1;     // odd leading dimension: conflict-free row and column access
 constexpr int SORT_MAX = 2048;    // largest 2m
-constexpr int VS_LEN = 1024;      // staged GEMV operand (max(n, m) doubles)
-constexpr size_t kSortBytes = (size_t)SORT_MAX * 2 * (8 + 4) + sizeof(unsigned) * (NW * 256 + 256 + 256);
+constexpr int VS_LEN = (QB_BP_PW == 32) ? 1024 : 960;   // staged GEMV operand (max(n, m) doubles)
+constexpr size_t kSortBytes = (size_t)SORT_MAX * (QB_BP_SORT_GLOBAL ? 1 : 2) * (8 + 4) + sizeof(unsigned) * (NW * 256 + 256 + 256);
 constexpr size_t kPanelBytes = sizeof(double) * PW * LDP;
 constexpr size_t kUnionBytes = kSortBytes > kPanelBytes ? kSortBytes : kPanelBytes;
 constexpr size_t kSmemBytes = kUnionBytes + sizeof(double) * (VS_LEN + NMAX + 16 + 2 * PW);
@@ -452,13 +465,15 @@ __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, cons
 // doubles (a 32-wide version needs 64 registers per array and spills at 3 CTAs / SM).
 constexpr int SW = 16;
 
-// Cholesky of the 16 x 16 block at (c0, c0) of the panel (P[t][r], t = column, r = row), warp 0, in place in shared
-// memory with ROLLED loops: a fully unrolled register version is ~3.4k straight-line instructions that one warp executes
-// once per call, i.e. it runs at instruction-fetch speed (measured 19 us per block vs ~3 us for this form).
+// Cholesky of the 16 x 16 block at (c0, c0) of the panel (P[t][r], t = column, r = row), warp 0; lane = row, the row
+// lives in registers.  The column loop is ROLLED around a rotating register file: a[0] is always the current column and
+// every step shifts the row one register to the left while it applies the rank-1 update, so all register indices are
+// static although the loop is not unrolled.  The body is ~100 instructions and stays in the instruction cache.  (A fully
+// unrolled version is ~1k straight-line instructions executed once per call; with three CTAs per SM in different phases
+// of this large kernel it ran at instruction-fetch-miss speed: 27 us per block in situ, phase profile of round 1.)  The
+// arithmetic and its order are those of the unrolled form, so results are bit-identical to it.
 // Columns/rows >= w (ragged last panel) are skipped.  rd[c0 + j] = 1 / l_jj.
 __device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, int w, int *info) {
-  // one copy of the unrolled register kernel (noinline: both sub-panels and every panel share the same ~1k instructions,
-  // which therefore stay in the instruction cache; measured 3.1k clocks per block warm vs 9k for a rolled shared-memory form)
   const int lane = threadIdx.x & 31;
   const int row = c0 + lane;
   const int wend = (w - c0 < SW) ? w - c0 : SW;
@@ -467,29 +482,29 @@ __device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, 
 #pragma unroll
   for (int c = 0; c < SW; c++) a[c] = (live && c < wend) ? ((c <= lane) ? Pn[(c0 + c) * LDP + row] : 0.0) : ((c == lane) ? 1.0 : 0.0);
   bool bad = false;
-#pragma unroll
+  __syncwarp();
+#pragma unroll 1
   for (int j = 0; j < SW; j++) {
-    const double pjj = __shfl_sync(0xffffffffu, a[j], j);
+    const double pjj = __shfl_sync(0xffffffffu, a[0], j);
     if (!(pjj > 0.0)) bad = true;
     const double inv = rsqrt(pjj);
-    if (lane == j) { a[j] = pjj * inv; rd[c0 + j] = inv; }
-    else if (lane > j) a[j] *= inv;
+    const double a0 = (lane == j) ? pjj * inv : a[0] * inv;     // lanes < j: upper triangle, never used
+    if (lane == j) rd[c0 + j] = inv;
+    if (live && lane >= j && j < wend) Pn[(c0 + j) * LDP + row] = a0;
 #pragma unroll
-    for (int c = 0; c < SW; c++) {
-      if (c > j) {   // constant bounds + predicate: see cta_potrf notes (a j-dependent bound leaves a[] in local memory)
-        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-        if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
-      }
+    for (int c = 1; c < SW; c++) {
+      const double lcj = __shfl_sync(0xffffffffu, a0, (j + c) & 31);
+      a[c - 1] = (lane >= j + c) ? fma(-a0, lcj, a[c]) : a[c];   // column j + c moves to register c - 1
     }
+    a[SW - 1] = 0.0;
   }
-#pragma unroll
-  for (int c = 0; c < SW; c++) if (live && c <= lane && c < wend) Pn[(c0 + c) * LDP + row] = a[c];
   if (bad && lane == 0 && info) *info = 1;
 }
 
-// rows r >= c0 + 16 of the panel: P[c0 + c][r] <- forward substitution against the 16 x 16 factor at (c0, c0)
+// rows below the sub-panel's diagonal block: P[c0 + c][r] <- forward substitution against the factor at (c0, c0)
 __device__ __forceinline__ void panel_solve16(double *Pn, const double *rd, int c0, int w, int rows) {
-  for (int r = c0 + SW + threadIdx.x; r < rows; r += NT) {
+  const int wsub = (w - c0 < SW) ? w - c0 : SW;       // the second sub-panel of a 24-column panel has 8 columns
+  for (int r = c0 + wsub + threadIdx.x; r < rows; r += NT) {
     double v[SW];
 #pragma unroll
     for (int c = 0; c < SW; c++) v[c] = (c0 + c < w) ? Pn[(c0 + c) * LDP + r] : 0.0;
@@ -531,6 +546,7 @@ __device__ __forceinline__ void panel_forward(const double *Pn, double *v, const
   if (warp == 0) {
     double vl = (lane < w) ? v[k0 + lane] : 0.0;
     const double rd = (lane < w) ? rdv[lane] : 1.0;
+    __syncwarp();   // re-join the warp: a split warp pays the slow collective path on every shuffle
     for (int j = 0; j < w; j++) {
       const double zj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
       if (lane == j) vl = zj;
@@ -555,7 +571,11 @@ __device__ __forceinline__ void cta_potrf(double *L, int ld, const double *src, 
   const int tid = threadIdx.x;
   double *Pn = S.panel;
   long long tq = clock64();
-#define PQ(k) do { if (pf && tid == 0) { const long long t_ = clock64(); pf[k] += t_ - tq; tq = t_; } } while (0)
+// Phase clocks: one predicated atomic, NO divergent region.  (An `if (tid == 0) { load; add; store }` body leaves lane 0 split
+// from the rest of warp 0 under independent thread scheduling; every __shfl_sync of the following single-warp phases then
+// takes the WARPSYNC.COLLECTIVE slow path -- measured 131k instead of 13.6k clocks per 16 x 16 diagonal block, which made
+// the profile of round 1 blame the wrong phase.)
+#define PQ(k) do { if (pf) { const long long t_ = clock64(); if (tid == NT - 1) atomicAdd(reinterpret_cast<unsigned long long *>(pf + (k)), (unsigned long long)(t_ - tq)); tq = t_; } } while (0)
   for (int k0 = 0; k0 < n; k0 += PW) {
     const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
     const bool first = (k0 == 0);
@@ -640,6 +660,7 @@ __device__ __forceinline__ void cta_chol_solve(const double *L, int ld, int n, c
     if (warp == 0) {
       double vl = (lane < w) ? v[k0 + lane] - S.rd[PW + lane] : 0.0;
       const double rd = (lane < w) ? rdiag_g[k0 + lane] : 1.0;
+      __syncwarp();
       for (int j = w - 1; j >= 0; j--) {
         const double dj = __shfl_sync(0xffffffffu, vl, j) * __shfl_sync(0xffffffffu, rd, j);
         if (lane == j) vl = dj;
@@ -851,19 +872,29 @@ __device__ __noinline__ void p_ls_build(const Args &P, int b, double *scratch) {
 
 // stable LSD radix sort of N <= SORT_MAX (key, val) pairs in shared memory; sorted pairs are written back to global
 __device__ __forceinline__ void p_sort(int N, unsigned long long *kg, unsigned int *vg, const Smem &S) {
-  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(S.u), *k1 = k0 + SORT_MAX;
-  unsigned int *v0 = reinterpret_cast<unsigned int *>(k1 + SORT_MAX), *v1 = v0 + SORT_MAX;
-  unsigned int *warp_cnt = v1 + SORT_MAX;            // [NW][256]
+  // ping-pong between ONE shared-memory buffer and the instance's global (kg, vg) arrays (L2-resident, 23 KB): a second
+  // shared buffer would cost the fourth CTA per SM
+#if QB_BP_SORT_GLOBAL
+  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(S.u);
+  unsigned int *v0 = reinterpret_cast<unsigned int *>(k0 + SORT_MAX);
+  unsigned int *warp_cnt = v0 + SORT_MAX;            // [NW][256]
+  unsigned long long *kalt = kg;
+  unsigned int *valt = vg;
+#else
+  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(S.u), *kalt = k0 + SORT_MAX;
+  unsigned int *v0 = reinterpret_cast<unsigned int *>(kalt + SORT_MAX), *valt = v0 + SORT_MAX;
+  unsigned int *warp_cnt = valt + SORT_MAX;          // [NW][256]
+#endif
   unsigned int *running = warp_cnt + NW * 256;       // [256]
   unsigned int *hist = running + 256;                // [256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < N; i += NT) { k0[i] = kg[i]; v0[i] = vg[i]; }
   __syncthreads();
-  unsigned long long *kin = k0, *kout = k1;
-  unsigned int *vin = v0, *vout = v1;
+  unsigned long long *kin = k0, *kout = kalt;
+  unsigned int *vin = v0, *vout = valt;
   for (int pass = 0; pass < 8; pass++) {
     const int shift = pass * 8;
-    hist[tid] = 0;   // NT == 256
+    for (int d = tid; d < 256; d += NT) hist[d] = 0;
     __syncthreads();
     for (int i = tid; i < N; i += NT) atomicAdd(&hist[(unsigned)(kin[i] >> shift) & 255u], 1u);
     __syncthreads();
@@ -897,11 +928,11 @@ __device__ __forceinline__ void p_sort(int N, unsigned long long *kg, unsigned i
         kout[off + rank] = k; vout[off + rank] = v;
       }
       __syncthreads();
-      {
+      for (int d = tid; d < 256; d += NT) {
         unsigned int t = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) t += warp_cnt[w * 256 + tid];
-        running[tid] += t;
+        for (int w = 0; w < NW; w++) t += warp_cnt[w * 256 + d];
+        running[d] += t;
       }
       __syncthreads();
     }
@@ -909,7 +940,7 @@ __device__ __forceinline__ void p_sort(int N, unsigned long long *kg, unsigned i
     unsigned int *tv = vin; vin = vout; vout = tv;
   }
   __syncthreads();
-  for (int i = tid; i < N; i += NT) { kg[i] = kin[i]; vg[i] = vin[i]; }
+  if (kin != kg) for (int i = tid; i < N; i += NT) { kg[i] = kin[i]; vg[i] = vin[i]; }
 }
 
 __device__ __noinline__ void p_ls_select(const Args &P, int b) {
@@ -991,8 +1022,8 @@ __device__ __noinline__ void p_store(const Args &P, int b, double *scratch) {
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-#define PH(k) do { if (P.prof && tid == 0) { const long long t_ = clock64(); P.prof[(size_t)b * 32 + (k)] += t_ - t_ph; t_ph = t_; } } while (0)
-__global__ void __launch_bounds__(NT, 3) kbp_solve(const Args P) {
+#define PH(k) do { if (P.prof) { const long long t_ = clock64(); if (tid == NT - 1) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof + (size_t)b * 32 + (k)), (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
+__global__ void __launch_bounds__(NT, (NT <= 192 ? 4 : 3)) kbp_solve(const Args P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[32];
   __shared__ int s_b;

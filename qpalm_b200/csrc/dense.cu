@@ -8,6 +8,8 @@
 //                                                   restated for L L' and panelised for the GPU)
 #include "dense.cuh"
 #include <vector>
+#include <map>
+#include <mutex>
 #include <stdlib.h>
 
 namespace qb {
@@ -732,6 +734,186 @@ __global__ void __launch_bounds__(NT) k_bwd_step(const double *__restrict__ L, i
 }
 }  // namespace trsv
 
+// ================================================================================================
+// Dataflow triangular solves (single matrix): ONE cooperative launch for forward + backward substitution.
+// CTA c owns the 128-row blocks c, c + G, ... : forward it accumulates  t_i = b_i - sum_{j<i} L_ij y_j  tile by tile,
+// consuming y_j as soon as its owner has published it (release/acquire flag in global memory), then forms
+// y_i = inv(L_ii) t_i and publishes it; backward likewise over the block columns in descending order.  The tile of the
+// next step is loaded into registers BEFORE the CTA waits for the flag, so the critical path per block is one L2 round
+// trip + two 128 x 128 matrix-vector products from registers / shared memory (about 2 us), instead of one kernel launch
+// per block (about 22 us).  The cooperative launch guarantees that all CTAs are co-resident, which the spin-waits need.
+// ================================================================================================
+namespace flow {
+constexpr int NB = 128, NT = 256;
+constexpr size_t kSmemBytes = sizeof(double) * (NB * NB + 6 * NB);
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all threads of the CTA return once *f == epoch
+__device__ __forceinline__ void wait_flag(const int *f, int epoch) {
+  if (threadIdx.x == 0) while (ld_acquire(f) != epoch) {}
+  __syncthreads();
+}
+// publish after the CTA's global writes
+__device__ __forceinline__ void publish(int *f, int epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); st_release(f, epoch); }
+}
+__device__ __forceinline__ void load_block_to_smem(double *Xs, const double *Xg) {
+  const double2 *src = reinterpret_cast<const double2 *>(Xg);
+  double2 *dst = reinterpret_cast<double2 *>(Xs);
+#pragma unroll 8
+  for (int idx = threadIdx.x; idx < NB * NB / 2; idx += NT) dst[idx] = __ldcg(src + idx);
+}
+
+__global__ void __launch_bounds__(NT, 1)
+k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X, double *v, int nblk, int *flags, int epoch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *Xs = reinterpret_cast<double *>(smem_raw);   // inverse of the current diagonal block, column-major
+  double *xs = Xs + NB * NB;                           // incoming solution block
+  double *scratch = xs + NB;                           // 2 * NB partial sums
+  double *rs = scratch + 2 * NB;                       // right-hand side of the diagonal solve
+  int *flag_f = flags, *flag_b = flags + nblk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid & (NB - 1), h = tid >> 7;
+  const int G = gridDim.x;
+
+  // ---------------- forward: L y = b ----------------
+  for (int i = blockIdx.x; i < nblk; i += G) {
+    load_block_to_smem(Xs, X + (size_t)i * NB * NB);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j = 0; j < i; j++) {
+      const double *Lp = L + (size_t)(i * NB + r) + (size_t)(j * NB + h * 64) * ld;
+      double t[64];
+#pragma unroll
+      for (int c = 0; c < 64; c++) t[c] = Lp[(size_t)c * ld];        // in flight while waiting for y_j
+      wait_flag(flag_f + j, epoch);
+      if (tid < NB) xs[tid] = __ldcg(v + (size_t)j * NB + tid);
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        a0 = fma(t[c], xs[h * 64 + c], a0);
+        a1 = fma(t[c + 1], xs[h * 64 + c + 1], a1);
+        a2 = fma(t[c + 2], xs[h * 64 + c + 2], a2);
+        a3 = fma(t[c + 3], xs[h * 64 + c + 3], a3);
+      }
+    }
+    scratch[h * NB + r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (h == 0) rs[r] = __ldcg(v + (size_t)i * NB + r) - (scratch[r] + scratch[NB + r]);
+    __syncthreads();
+    {   // y_i = inv(L_ii) rs   (Xs lower triangular, zeros above)
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+      const int c0 = h * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        b0 = fma(Xs[r + NB * (c0 + c)], rs[c0 + c], b0);
+        b1 = fma(Xs[r + NB * (c0 + c + 1)], rs[c0 + c + 1], b1);
+        b2 = fma(Xs[r + NB * (c0 + c + 2)], rs[c0 + c + 2], b2);
+        b3 = fma(Xs[r + NB * (c0 + c + 3)], rs[c0 + c + 3], b3);
+      }
+      scratch[h * NB + r] = (b0 + b1) + (b2 + b3);
+      __syncthreads();
+      if (h == 0) v[(size_t)i * NB + r] = scratch[r] + scratch[NB + r];
+    }
+    publish(flag_f + i, epoch);
+  }
+
+  // ---------------- backward: L' x = y ----------------
+  const int last = blockIdx.x + ((nblk - 1 - blockIdx.x) / G) * G;      // this CTA's highest block
+  for (int j = last; j >= 0; j -= G) {
+    __syncthreads();
+    load_block_to_smem(Xs, X + (size_t)j * NB * NB);
+    double acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc[u] = 0.0;
+    for (int i = nblk - 1; i > j; i--) {
+      const double *Lp = L + (size_t)(i * NB + lane) + (size_t)(j * NB + warp * 16) * ld;
+      double t[16][4];
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) t[u][q] = Lp[(size_t)u * ld + 32 * q];
+      wait_flag(flag_b + i, epoch);
+      if (tid < NB) xs[tid] = __ldcg(v + (size_t)i * NB + tid);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double dv = xs[lane + 32 * q];
+#pragma unroll
+        for (int u = 0; u < 16; u++) acc[u] = fma(t[u][q], dv, acc[u]);
+      }
+    }
+    // the forward value y_j was published (fenced) by this CTA; every consumer of it finished before x_{j+1} appeared
+    if (j == nblk - 1) wait_flag(flag_f + j, epoch);   // uniform: makes the smem reuse below safe in the degenerate case
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const double sacc = warp_sum(acc[u]);
+      if (lane == 0) rs[warp * 16 + u] = __ldcg(v + (size_t)j * NB + warp * 16 + u) - sacc;
+    }
+    __syncthreads();
+    // x_j = inv(L_jj)' rs : column c of Xs dotted with rs
+    for (int c = warp; c < NB; c += NT / 32) {
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) a = fma(Xs[lane + 32 * q + NB * c], rs[lane + 32 * q], a);
+      a = warp_sum(a);
+      if (lane == 0) v[(size_t)j * NB + c] = a;
+    }
+    publish(flag_b + j, epoch);
+  }
+}
+
+struct FlowState { int *flags = nullptr; int cap = 0; int epoch = 0; int max_grid = 0; };
+static std::mutex g_flow_mu;
+static std::map<cudaStream_t, FlowState> g_flow;
+}  // namespace flow
+
+// returns 0 when the dataflow solve ran, 1 when it is not available (caller falls back to the per-block launches), < 0 on error
+static int chol_solve_flow(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v) {
+  static const bool off = getenv("QPALM_B200_NO_FLOW_SOLVE") != nullptr;
+  if (off) return 1;
+  const int nblk = npad / kPanel;
+  flow::FlowState st;
+  {
+    std::lock_guard<std::mutex> lk(flow::g_flow_mu);
+    flow::FlowState &ref = flow::g_flow[s];
+    if (ref.max_grid == 0) {
+      int dev = 0, coop = 0, sms = 0, per_sm = 0;
+      QB_CUDA_TRY(cudaGetDevice(&dev));
+      QB_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      QB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      QB_CUDA_TRY(cudaFuncSetAttribute(flow::k_solve_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flow::kSmemBytes));
+      QB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow::k_solve_flow, flow::NT, flow::kSmemBytes));
+      ref.max_grid = coop ? sms * per_sm : -1;
+    }
+    if (ref.max_grid <= 0) return 1;
+    if (ref.cap < 2 * nblk) {
+      if (ref.flags) QB_CUDA_TRY(cudaFree(ref.flags));
+      ref.cap = 2 * nblk + 64;
+      QB_CUDA_TRY(cudaMalloc(&ref.flags, sizeof(int) * ref.cap));
+      QB_CUDA_TRY(cudaMemsetAsync(ref.flags, 0, sizeof(int) * ref.cap, s));
+      ref.epoch = 0;
+    }
+    ref.epoch++;
+    st = ref;
+  }
+  int grid = nblk < st.max_grid ? nblk : st.max_grid;
+  int nblk_arg = nblk, ld_arg = ld, epoch = st.epoch;
+  int *flags = st.flags;
+  void *args[] = {(void *)&L, (void *)&ld_arg, (void *)&invdiag, (void *)&v, (void *)&nblk_arg, (void *)&flags, (void *)&epoch};
+  const bool prof = g_prof_on && prof_begin("flow::k_solve_flow", s);
+  QB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)flow::k_solve_flow, dim3(grid), dim3(flow::NT), args, flow::kSmemBytes, s));
+  ++g_kernel_launches;
+  if (prof) prof_end(s);
+  return 0;
+}
+
 int chol_solve_batched(cudaStream_t s, int nb, int npad, const double *L, int ld, long long sL, const double *invdiag,
                        long long sX, double *v, long long sV, const int *mask) {
   const int nblk = npad / kPanel;
@@ -746,6 +928,10 @@ int chol_solve_batched(cudaStream_t s, int nb, int npad, const double *L, int ld
   return 0;
 }
 int chol_solve(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v) {
+  if (npad > 2 * kPanel) {
+    const int rc = chol_solve_flow(s, npad, L, ld, invdiag, v);
+    if (rc <= 0) return -rc;
+  }
   return chol_solve_batched(s, 1, npad, L, ld, 0, invdiag, 0, v, 0, nullptr);
 }
 
