@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: parity tests, smoke, bench (both arms), kernel launch lists under ncu, ncu --set full of the two
+# One gpurun call: parity tests, smoke, bench (both arms), kernel launch lists under ncu, ncu --set full of the
 # dominant kernels.  Logs go to gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
@@ -10,6 +10,9 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 ( time timeout 1200 python bench.py --steps 3 --warmup 3 ) > gpurun_out/bench.log 2>&1
 ( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/bench_ref.log 2>&1
 ( time timeout 900 python bench.py --workload dense --steps 2 --warmup 3 ) > gpurun_out/bench_dense.log 2>&1
+python tools/batch_phases.py 512 > gpurun_out/batch_phases.txt 2>&1
+python tools/microbench.py > gpurun_out/microbench.txt 2>&1
+python tools/prof_dense.py 8000 potrf_prof > gpurun_out/potrf_prof.txt 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_batch.csv \
    python bench.py --steps 1 --warmup 1 --no-dense --no-cpu > gpurun_out/ncu_batch.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_dense.csv \
@@ -18,5 +21,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:kbp_
    python bench.py --steps 1 --warmup 1 --no-dense --no-cpu > gpurun_out/ncu_full_batch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dgemm_nt -s 200 -c 1 -f -o gpurun_out/full_k_dgemm_nt \
    python bench.py --workload dense --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full_dense.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_diag_block -s 40 -c 1 -f -o gpurun_out/full_k_diag_block \
+   python tools/prof_dense.py 8000 potrf > gpurun_out/ncu_full_diag.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_flow -s 2 -c 1 -f -o gpurun_out/full_k_solve_flow \
+   python bench.py --workload dense --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full_flow.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; tail -2 gpurun_out/bench.log; tail -2 gpurun_out/bench_ref.log; tail -2 gpurun_out/bench_dense.log
 ls -la gpurun_out
