@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p build
 pids=()
 for f in dense kernels api ops batch batchp prof shard sparse sparse_sym qps; do
-  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ engine.cuh -nt build/$f.o ] || [ dense.cuh -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ batch.cuh -nt build/$f.o ] || [ sparse.cuh -nt build/$f.o ] || [ sparse_host.h -nt build/$f.o ] || [ ../../include/qpalm_b200.h -nt build/$f.o ]; then
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ engine.cuh -nt build/$f.o ] || [ dense.cuh -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ batch.cuh -nt build/$f.o ] || [ sparse.cuh -nt build/$f.o ] || [ sparse_host.h -nt build/$f.o ] || [ chol32.cuh -nt build/$f.o ] || [ ../../include/qpalm_b200.h -nt build/$f.o ]; then
     $NVCC $FLAGS -c $f.cu -o build/$f.o &
     pids+=($!)
   fi

@@ -7,6 +7,7 @@
 //   cholmod_updown                 -> chol_updown  (rank-k recurrence of t_cholmod_updown_numkr.c:289-376
 //                                                   restated for L L' and panelised for the GPU)
 #include "dense.cuh"
+#include "chol32.cuh"
 #include <vector>
 #include <map>
 #include <mutex>
@@ -192,44 +193,7 @@ constexpr int NB = 128, DS = 129, NT = 256, SB = 32, XS = 33, PS = 100;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + SB * XS + (NB - SB) * XS + SB * PS + NB) + 16;
 
-// Branch-free sqrt(p) and 1/sqrt(p) for a normal positive p: hardware 1/sqrt seed (about 22 bits), two coupled Newton
-// steps on (g, h) ~ (sqrt p, 1/(2 sqrt p)), Markstein's final correction for g (correctly rounded sqrt), then the
-// reciprocal of g from the seed 2h with two FMA corrections.  Same values as sqrt() and 1.0 / sqrt() of the reference
-// arithmetic for normal inputs, but without their slow-path calls, so the 32-column factorization stays one straight-line
-// block the scheduler can interleave.  A non-positive p gives NaN (flagged by the caller).
-__device__ __forceinline__ void sqrt_and_rcp(double p, double &g, double &x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-  g = p * y;
-  double h = 0.5 * y;
-#pragma unroll
-  for (int it = 0; it < 2; it++) {
-    const double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-  }
-  g = fma(fma(-g, g, p), h, g);
-  x = h + h;
-#pragma unroll
-  for (int it = 0; it < 2; it++) x = fma(x, fma(-g, x, 1.0), x);
-}
-
-template <int J>
-__device__ __forceinline__ void fstep(double (&a)[SB], const int lane, double &dl, double &dinv, int &badcol) {
-  const double pjj = __shfl_sync(FULL, a[J], J);
-  double ljj, inv;
-  sqrt_and_rcp(pjj, ljj, inv);
-  const double lij = a[J] * inv;           // L(row, J)
-#pragma unroll
-  for (int c = J + 1; c < SB; c++) {
-    const double lcj = __shfl_sync(FULL, a[J], c) * inv;   // L(c, J), the value lane c itself stores
-    a[c] = fma(-lij, lcj, a[c]);
-  }
-  if (!(pjj > 0.0) && badcol < 0) badcol = J;
-  a[J] = lij;
-  if (lane == J) { dl = ljj; dinv = inv; }
-  if constexpr (J + 1 < SB) fstep<J + 1>(a, lane, dl, dinv, badcol);
-}
+using chol32::fstep;
 
 // one warp: in-register Cholesky of the 32 x 32 block at (base, base); strictly-lower part of L back into As,
 // 1/L(j,j) onto the diagonal of As, L(j,j) into ldiag.

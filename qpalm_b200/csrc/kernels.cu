@@ -690,28 +690,31 @@ __global__ void __launch_bounds__(NT) k_hist(const unsigned long long *__restric
   __syncthreads();
   if (threadIdx.x < 256) hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
-// exclusive scan of hist[0 .. total) in place (digit-major, tile-minor), one CTA
+// exclusive scan of hist[0 .. total) in place (digit-major, tile-minor), one CTA: every warp scans one contiguous
+// segment with a running carry (coalesced, no CTA barriers inside the loop), the 32 segment totals are combined once and
+// added back in a second sweep over the warp's own writes.  (The round-1 version walked the array in 1024-entry chunks
+// with three CTA barriers per chunk: 82 us at 2m = 717k against ~10 us for this form.)
 __global__ void __launch_bounds__(1024) k_scan(unsigned int *hist, int total) {
-  __shared__ unsigned int wsum[32];
-  __shared__ unsigned int carry;
+  __shared__ unsigned int wtot[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry = 0;
-  __syncthreads();
-  for (int start = 0; start < total; start += 1024) {
-    const int i = start + tid;
-    const unsigned int v = (i < total) ? hist[i] : 0u;
+  const int seg = ((total + 31) / 32 + 31) & ~31;          // per-warp segment, a multiple of 32
+  const int begin = warp * seg, end = min(begin + seg, total);
+  unsigned int carry = 0;
+  for (int i0 = begin; i0 < begin + seg; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned int v = (i < end) ? hist[i] : 0u;
     unsigned int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    unsigned int woff = 0;
-    for (int w = 0; w < warp; w++) woff += wsum[w];
-    if (i < total) hist[i] = carry + woff + inc - v;
-    __syncthreads();
-    if (tid == 1023) carry += woff + inc;
-    __syncthreads();
+    if (i < end) hist[i] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
+  if (lane == 0) wtot[warp] = carry;
+  __syncthreads();
+  unsigned int off = 0;
+  for (int w = 0; w < warp; w++) off += wtot[w];
+  if (off)
+    for (int i = begin + lane; i < end; i += 32) hist[i] += off;
 }
 __global__ void __launch_bounds__(NT) k_scatter(const unsigned long long *__restrict__ kin, const unsigned int *__restrict__ vin,
                                                 unsigned long long *kout, unsigned int *vout, int N, int shift,

@@ -16,6 +16,7 @@
 // Rank-k update/downdate: k_ud_mark marks the etree paths, k_ud_sweep walks them (one CTA, columns in ascending order).
 #include "sparse.cuh"
 #include "sparse_host.h"
+#include "chol32.cuh"
 
 #include <string.h>
 #include <vector>
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(256) k_mf_extend(SpDev d, double *panels, doub
   }
 }
 
-// 32 x 32 (w x w) Cholesky of the diagonal block kb of every front of the level: one warp per front, lane = row
+// 32 x 32 (w x w) Cholesky of the diagonal block kb of every front of the level: one warp per front, lane = row.
+// The row lives in registers with static indices (chol32.cuh: template-unrolled columns, branch-free sqrt/reciprocal);
+// rows / columns >= w are an identity pad.
 __global__ void __launch_bounds__(32) k_mf_diag(SpDev d, double *panels, int lvl_begin, int kb, int *info) {
   const int s = d.lvl_sn[lvl_begin + blockIdx.x];
   const int f = d.first[s], ns = d.first[s + 1] - f, nf = ns + d.rows_off[s + 1] - d.rows_off[s];
@@ -227,22 +230,13 @@ __global__ void __launch_bounds__(32) k_mf_diag(SpDev d, double *panels, int lvl
   double row[32];
 #pragma unroll
   for (int j = 0; j < 32; j++) row[j] = (lane < w && j <= lane) ? B[(size_t)lane + (size_t)j * nf] : ((j == lane) ? 1.0 : 0.0);
-  bool bad = false;
+  double dl = 1.0, dinv = 1.0;
+  int badcol = -1;
+  chol32::fstep<0>(row, lane, dl, dinv, badcol);
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
-    const double djj = __shfl_sync(0xffffffffu, row[j], j);
-    if (!(djj > 0.0) && j < w) bad = true;
-    const double l = sqrt(djj);
-    if (lane == j) row[j] = l; else if (lane > j) row[j] = row[j] / l;
-#pragma unroll
-    for (int jj = j + 1; jj < 32; jj++) {
-      const double ljj = __shfl_sync(0xffffffffu, row[j], jj);
-      if (lane >= jj) row[jj] = fma(-row[j], ljj, row[jj]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; j++) if (lane < w && j <= lane) B[(size_t)lane + (size_t)j * nf] = row[j];
-  if (bad && lane == 0) atomicExch(info, 1 + f + k0);
+  for (int j = 0; j < 32; j++) if (lane < w && j < lane) B[(size_t)lane + (size_t)j * nf] = row[j];
+  if (lane < w) B[(size_t)lane + (size_t)lane * nf] = dl;
+  if (badcol >= 0 && badcol < w && lane == 0) atomicExch(info, 1 + f + k0);
 }
 
 // rows below diagonal block kb: X <- X * Lkk^{-T}, one thread per row
@@ -258,7 +252,9 @@ __global__ void __launch_bounds__(128) k_mf_trsm(SpDev d, double *panels, int lv
   double *P = panels + d.panel_off[s];
   for (int t = threadIdx.x; t < 32 * 32; t += 128) {
     const int r = t & 31, c = t >> 5;
-    Ls[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+    double v = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+    if (r == c) v = 1.0 / v;          // the diagonal is stored inverted: one division per column instead of one per element
+    Ls[r][c] = v;
   }
   __syncthreads();
   const int i = i0 + threadIdx.x;
@@ -271,7 +267,7 @@ __global__ void __launch_bounds__(128) k_mf_trsm(SpDev d, double *panels, int lv
     double a = x[t];
 #pragma unroll
     for (int u = 0; u < t; u++) a = fma(-x[u], Ls[t][u], a);
-    x[t] = a / Ls[t][t];
+    x[t] = a * Ls[t][t];
   }
 #pragma unroll
   for (int t = 0; t < 32; t++) if (t < w) P[(size_t)i + (size_t)(k0 + t) * nf] = x[t];
@@ -414,9 +410,18 @@ __global__ void k_sp_permute_out(SpDev d, const double *__restrict__ v, double *
 
 // forward: L y = b.  f (shared, nf) = [b_s ; 0] + children's update vectors; solve the ns x ns triangle in 32-column
 // blocks; u_s = f[ns..) is handed to the parent.
+// x / l from the correctly rounded reciprocal r = 1 / l: one multiply and two FMAs, no slow-path branch; the residual
+// correction makes the quotient correctly rounded (Markstein), i.e. the value a division returns -- the ill-conditioned
+// known-answer problems (tests/src/test_dua_inf_qp.c) flip iteration counts on a one-ulp difference here.
+__device__ __forceinline__ double div_by_rcp(double x, double l, double r) {
+  const double q = x * r;
+  return fma(fma(-q, l, x), r, q);
+}
+
 __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restrict__ panels, double *v, double *uvec, int lvl_begin) {
   extern __shared__ double fsh[];
   __shared__ double blk[32][33];
+  __shared__ double dgl[32];
   const int s = d.lvl_sn[lvl_begin + blockIdx.x];
   const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
   const double *P = panels + d.panel_off[s];
@@ -433,23 +438,35 @@ __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restric
     const int w = min(32, ns - k0);
     for (int t = tid; t < 32 * 32; t += blockDim.x) {
       const int r = t & 31, c = t >> 5;
-      blk[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+      double e = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+      if (r == c) { dgl[r] = e; e = 1.0 / e; }     // inverted diagonal (one division per column, off the serial chain)
+      blk[r][c] = e;
     }
     __syncthreads();
     if (tid < 32) {
       double x = (tid < w) ? fsh[k0 + tid] : 0.0;
 #pragma unroll
       for (int j = 0; j < 32; j++) {
-        const double xj = __shfl_sync(0xffffffffu, x, j) / blk[j][j];
+        const double xj = div_by_rcp(__shfl_sync(0xffffffffu, x, j), dgl[j], blk[j][j]);
         if (tid == j) x = xj; else if (tid > j) x = fma(-blk[tid][j], xj, x);
       }
       if (tid < w) fsh[k0 + tid] = x;
     }
     __syncthreads();
     for (int i = k0 + w + tid; i < nf; i += blockDim.x) {
-      double a = fsh[i];
-      for (int t = 0; t < w; t++) a = fma(-P[(size_t)i + (size_t)(k0 + t) * nf], fsh[k0 + t], a);
-      fsh[i] = a;
+      // 8 independent loads in flight per thread (a rolled loop pays one L2 round trip per column)
+      const double *Pi = P + (size_t)i + (size_t)k0 * nf;
+      double a0 = fsh[i], a1 = 0.0;
+      int t = 0;
+      for (; t + 8 <= w; t += 8) {
+        double pv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) pv[u] = Pi[(size_t)(t + u) * nf];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) { a0 = fma(-pv[u], fsh[k0 + t + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + t + u + 1], a1); }
+      }
+      for (; t < w; t++) a0 = fma(-Pi[(size_t)t * nf], fsh[k0 + t], a0);
+      fsh[i] = a0 + a1;
     }
     __syncthreads();
   }
@@ -461,6 +478,7 @@ __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restric
 __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restrict__ panels, double *v, int lvl_begin) {
   extern __shared__ double fsh[];
   __shared__ double blk[32][33];
+  __shared__ double dgl[32];
   const int s = d.lvl_sn[lvl_begin + blockIdx.x];
   const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
   const double *P = panels + d.panel_off[s];
@@ -472,13 +490,20 @@ __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restric
     const int k0 = kb * 32, w = min(32, ns - k0);
     for (int t = tid; t < 32 * 32; t += blockDim.x) {
       const int r = t & 31, c = t >> 5;
-      blk[r][c] = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+      double e = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+      if (r == c) { dgl[r] = e; e = 1.0 / e; }
+      blk[r][c] = e;
     }
     for (int t = warp; t < w; t += nw) {
       const double *col = P + (size_t)(k0 + t) * nf;
-      double a = 0.0;
-      for (int i = k0 + w + lane; i < nf; i += 32) a = fma(col[i], fsh[i], a);
-      a = warp_sum(a);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int i = k0 + w + lane;
+      for (; i + 96 < nf; i += 128) {      // four independent loads in flight per lane
+        a0 = fma(col[i], fsh[i], a0); a1 = fma(col[i + 32], fsh[i + 32], a1);
+        a2 = fma(col[i + 64], fsh[i + 64], a2); a3 = fma(col[i + 96], fsh[i + 96], a3);
+      }
+      for (; i < nf; i += 32) a0 = fma(col[i], fsh[i], a0);
+      const double a = warp_sum((a0 + a1) + (a2 + a3));
       if (lane == 0) fsh[k0 + t] -= a;
     }
     __syncthreads();
@@ -486,7 +511,7 @@ __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restric
       double x = (tid < w) ? fsh[k0 + tid] : 0.0;
 #pragma unroll
       for (int j = 31; j >= 0; j--) {
-        const double xj = __shfl_sync(0xffffffffu, x, j) / blk[j][j];
+        const double xj = div_by_rcp(__shfl_sync(0xffffffffu, x, j), dgl[j], blk[j][j]);
         if (tid == j) x = xj; else if (tid < j) x = fma(-blk[j][tid], xj, x);
       }
       if (tid < w) fsh[k0 + tid] = x;

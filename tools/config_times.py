@@ -60,4 +60,5 @@ if "c2" in which:
     report(f"C2 stand-in (SYNTHETIC grid QP via QPS) n={n} m={pr.m}", p)
 if "c5" in which:
     n5 = int(os.environ.get("C5_N", "5000"))
-    report(f"C5 nonconvex random QP n={n5} m={2 * n5}", problems.nonconvex_random_qp(n5, 2 * n5, seed=0))
+    seed5 = int(os.environ.get("C5_SEED", "1"))   # seed 0 and 2 make the REFERENCE return NaN at n=5000 (see profiles/r01d_config_times_*)
+    report(f"C5 nonconvex random QP n={n5} m={2 * n5} seed={seed5}", problems.nonconvex_random_qp(n5, 2 * n5, seed=seed5))
