@@ -11,6 +11,7 @@
 // Ruiz scaling: D and E depend on A only and are shared; the cost scaling c = 1/max(1, |D q|inf) (scaling.c:84-89)
 // depends on q and is per instance, so the shared scaled Hessian is kept as D Q D and c is applied on the fly.
 #include "batch.cuh"
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 
@@ -917,7 +918,15 @@ extern "C" int qpalm_b200_batch_solve_resident(QPALMB200Batch *B, c_int nb_, dou
   if (persistent) {
     if (!batchp_supported(n, m)) { fprintf(stderr, "[qpalm_b200] batch: shapes n=%d m=%d do not fit the persistent engine\n", n, m); return 1; }
     QB_CUDA_TRY(cudaEventRecord(B->ev0, s));
-    if (int r = batchp_solve(B, nb)) return r;
+    // shape choice (batchp.cu header): the 4-CTA/SM build only when it turns two waves into one
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; QB_CUDA_TRY(cudaGetDevice(&dev)); QB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+    static const char *shape_env = getenv("QPALM_B200_BATCH_SHAPE");   // "3" / "4" force a shape (A/B measurements)
+    bool four = nb > 3 * num_sms && nb <= 4 * num_sms;
+    if (shape_env && shape_env[0] == '3') four = false;
+    if (shape_env && shape_env[0] == '4') four = true;
+    if (four && !batchp4_supported(n, m)) four = false;
+    if (int r = four ? batchp4_solve(B, nb) : batchp_solve(B, nb)) return r;
     QB_CUDA_TRY(cudaEventRecord(B->ev1, s));
     QB_CUDA_TRY(cudaEventSynchronize(B->ev1));
     float msp = 0; cudaEventElapsedTime(&msp, B->ev0, B->ev1);

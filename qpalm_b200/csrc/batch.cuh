@@ -61,4 +61,7 @@ namespace qb {
 // persistent engine (batchp.cu): true when the shapes fit its shared-memory plan
 bool batchp_supported(int n, int m);
 int batchp_solve(QPALMB200Batch *B, int nb);
+// the same engine compiled in its 4-CTAs-per-SM shape (batchp.cu with -DQB_BP_VARIANT4)
+bool batchp4_supported(int n, int m);
+int batchp4_solve(QPALMB200Batch *B, int nb);
 }  // namespace qb

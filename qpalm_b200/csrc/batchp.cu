@@ -24,13 +24,30 @@
 
 using namespace qb;
 
-namespace qb {
-namespace bp {
-
-// Build-time shape of a CTA.  Default: 8 warps, 32-column panel, both sort buffers in shared memory = 80 registers x 256
-// threads, 72 KB -> 3 CTAs / SM.  The 4-CTA shape (-DQB_BP_NT=192 -DQB_BP_PW=24 -DQB_BP_SORT_GLOBAL=1: 55 KB) was measured
-// in round 1: it holds the whole 512-instance sweep in one wave but the two extra panels per factorization and the
-// smaller CTAs cost as much as the second wave saves (138.6 ms either way), so it is not the default.
+// Build-time shape of a CTA; this file is compiled twice (build.sh):
+//   default            8 warps, 32-column panel, both sort buffers in shared memory: 80 registers x 256 threads, 72 KB
+//                      -> 3 CTAs / SM (444 slots on a B200).  Best per-wave throughput (444 instances in 93 ms).
+//   -DQB_BP_VARIANT4   8 warps, 24-column panel (sub-panels 16 + 8), one sort buffer in shared memory and the other in the
+//                      instance's global arrays, registers capped at 64: 55 KB -> 4 CTAs / SM (592 slots).  Slower per
+//                      wave (592 instances in 130 ms) but the BASELINE sweep of 512 instances per GPU fits in ONE wave:
+//                      127 ms instead of 139 ms with the 68-instance tail of the default shape.  batch.cu picks it when
+//                      3 * SMs < nb <= 4 * SMs.
+// Other shapes measured in round 1 (512 instances): 192 threads / PW 24 / 4 per SM 138.6 ms; 192 / PW 16 / 4 per SM
+// 147.7 ms; 256 / PW 16 / 64 regs / 4 per SM 133.0 ms; 192 threads / PW 32 / 3 per SM 192.5 ms (fewer threads per CTA
+// cost more than the extra occupancy buys).
+#ifdef QB_BP_VARIANT4
+#define QB_BP_NAMESPACE bp4
+#define QB_BP_SUPPORTED batchp4_supported
+#define QB_BP_SOLVE batchp4_solve
+#define QB_BP_NT 256
+#define QB_BP_PW 24
+#define QB_BP_SORT_GLOBAL 1
+#define QB_BP_MINB 4
+#else
+#define QB_BP_NAMESPACE bp
+#define QB_BP_SUPPORTED batchp_supported
+#define QB_BP_SOLVE batchp_solve
+#endif
 #ifndef QB_BP_NT
 #define QB_BP_NT 256
 #endif
@@ -40,6 +57,9 @@ namespace bp {
 #ifndef QB_BP_SORT_GLOBAL
 #define QB_BP_SORT_GLOBAL 0
 #endif
+namespace qb {
+namespace QB_BP_NAMESPACE {
+
 constexpr int NT = QB_BP_NT, NW = NT / 32;
 constexpr int PW = QB_BP_PW;      // panel width (sub-panels of 16 + 8 columns)
 constexpr int NMAX = 240;         // largest n of this engine (panel = PW x LDP doubles of shared memory)
@@ -1023,7 +1043,10 @@ __device__ __noinline__ void p_store(const Args &P, int b, double *scratch) {
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
 #define PH(k) do { if (P.prof) { const long long t_ = clock64(); if (tid == NT - 1) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof + (size_t)b * 32 + (k)), (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
-__global__ void __launch_bounds__(NT, (NT <= 192 ? 4 : 3)) kbp_solve(const Args P) {
+#ifndef QB_BP_MINB
+#define QB_BP_MINB (QB_BP_NT <= 192 ? 4 : 3)
+#endif
+__global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[32];
   __shared__ int s_b;
@@ -1137,14 +1160,14 @@ __global__ void __launch_bounds__(NT, (NT <= 192 ? 4 : 3)) kbp_solve(const Args 
   }
 }
 
-}  // namespace bp
+}  // namespace QB_BP_NAMESPACE (bp / bp4)
 
-bool batchp_supported(int n, int m) {
-  return n >= 1 && n <= bp::NMAX && m >= 1 && 2 * m <= bp::SORT_MAX && m <= bp::VS_LEN;
+bool QB_BP_SUPPORTED(int n, int m) {
+  return n >= 1 && n <= QB_BP_NAMESPACE::NMAX && m >= 1 && 2 * m <= QB_BP_NAMESPACE::SORT_MAX && m <= QB_BP_NAMESPACE::VS_LEN;
 }
 
-int batchp_solve(QPALMB200Batch *B, int nb) {
-  using namespace bp;
+int QB_BP_SOLVE(QPALMB200Batch *B, int nb) {
+  using namespace QB_BP_NAMESPACE;
   Engine *e = B->shared;
   Args P;
   memset(&P, 0, sizeof(P));

@@ -13,6 +13,11 @@ for f in dense kernels api ops batch batchp prof shard sparse sparse_sym qps; do
     pids+=($!)
   fi
 done
+# the persistent batch engine a second time in its 4-CTAs-per-SM shape (see the header of batchp.cu)
+if [ ! -f build/batchp4.o ] || [ batchp.cu -nt build/batchp4.o ] || [ batch.cuh -nt build/batchp4.o ] || [ common.cuh -nt build/batchp4.o ] || [ engine.cuh -nt build/batchp4.o ]; then
+  $NVCC $FLAGS -DQB_BP_VARIANT4 -c batchp.cu -o build/batchp4.o &
+  pids+=($!)
+fi
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o ../libqpalm_b200.so build/dense.o build/kernels.o build/api.o build/ops.o build/batch.o build/batchp.o build/prof.o build/shard.o build/sparse.o build/sparse_sym.o build/qps.o -lcudart -ldl
+$NVCC -shared -o ../libqpalm_b200.so build/dense.o build/kernels.o build/api.o build/ops.o build/batch.o build/batchp.o build/batchp4.o build/prof.o build/shard.o build/sparse.o build/sparse_sym.o build/qps.o -lcudart -ldl
 echo "built $(cd .. && pwd)/libqpalm_b200.so"
