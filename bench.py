@@ -259,8 +259,9 @@ def hbm_roofline(lib, n, m):
 # one kernel; in the lock-step engine the single-CTA diagonal-block factorisation leads (39 %)
 DOMINANT_KERNEL = {"persistent": "kbp_solve", "lockstep": "k_diag_block"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the `ncu --set full` capture of this command at the default
-# --batch 512 (profiles/r01d_ncu_full_kbp_solve.txt: 34.66 GB read + 38.37 GB written)
-NCU_TRAFFIC_BYTES = {("kbp_solve", 512): 34.655802e9 + 38.369465e9}
+# --batch 512 (profiles/r01e_ncu_full_kbp_solve.txt, the 4-CTA/SM shape the dispatcher picks for 512: 56.02 GB read + 58.58 GB written;
+# the 3-CTA/SM shape moved 34.66 + 38.37 GB, profiles/r01d_ncu_full_kbp_solve.txt)
+NCU_TRAFFIC_BYTES = {("kbp_solve", 512): 56.016316e9 + 58.581683e9}
 
 
 def batch_algorithmic_bytes(n, m, stats):
@@ -289,7 +290,7 @@ def batch_roofline(n, m, nb, r, steps):
         note = "per launch: every instance's 128 x 128 diagonal block read + written, inverse written (upper bound: masked instances skip)"
     ach = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": r["dominant"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": NCU_TRAFFIC_BYTES.get((r["dominant"], nb)), "traffic_source": "profiles/r01d_ncu_full_kbp_solve.txt",
+            "traffic": NCU_TRAFFIC_BYTES.get((r["dominant"], nb)), "traffic_source": "profiles/r01e_ncu_full_kbp_solve.txt",
             "peak_source": src, "launches_timed": launches, "ms_per_launch": per_launch_ms, "share_of_step": ms / max(r["dev_ms"], 1e-9),
             "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
 
