@@ -24,8 +24,9 @@ long long g_kernel_launches = 0;
 // fragment loads: lane -> (k = lane & 3, row = lane >> 2) hits 16 distinct 8-byte banks per half warp).
 // ================================================================================================
 namespace gemm {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, SROW = BM + 4;
-constexpr size_t kSmemBytes = sizeof(double) * 2 * STAGES * BK * SROW;
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3;
+template <int BM_> constexpr size_t smem_bytes() { return sizeof(double) * STAGES * BK * ((BM_ + 4) + (BN + 4)); }
+constexpr size_t kSmemBytes = smem_bytes<BM>();
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -41,42 +42,52 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
       : "d"(a), "d"(b));
 }
 
+// BM_ = 128: CTA tile 128 x 128, warps 2 x 4, warp tile 64 x 32.  BM_ = 64: CTA tile 64 x 128, warps 1 x 8, warp tile
+// 64 x 16 -- twice as many CTAs of half the work each, for the panel solves and in-block updates of the Cholesky chain
+// whose 128-row grids fill less than one wave of the 148 SMs.
+template <int BM_>
 __global__ void __launch_bounds__(256, 1)
 k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
            double *C, int ldc, double alpha, double beta, int lower_only,
            long long sA, long long sB, long long sC, const int *Kz, const int *maskz) {
+  constexpr int SROWA = BM_ + 4, SROWB = BN + 4;
+  constexpr int WM = BM_ / 64, WN = 8 / WM, NF = BN / (8 * WN);   // warps along M / N, n-fragments per warp
   // blockIdx.z: batch instance (strides sA/sB/sC, optional per-instance K and activity mask)
   const int bm = blockIdx.x, bn = blockIdx.y;
-  if (lower_only && bn > bm) return;
+  if (lower_only && bn * BN >= (bm + 1) * BM_) return;
   if (maskz && !maskz[blockIdx.z]) return;
   if (Kz) K = Kz[blockIdx.z];
   if (K <= 0 && beta == 1.0) return;
   A += (size_t)blockIdx.z * sA; B += (size_t)blockIdx.z * sB; C += (size_t)blockIdx.z * sC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef double Tile[BK][SROW];
-  Tile *As = reinterpret_cast<Tile *>(smem_raw);
-  Tile *Bs = reinterpret_cast<Tile *>(smem_raw + sizeof(double) * STAGES * BK * SROW);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
-  const double *Ag = A + (size_t)bm * BM;
+  typedef double TileA[BK][SROWA];
+  typedef double TileB[BK][SROWB];
+  TileA *As = reinterpret_cast<TileA *>(smem_raw);
+  TileB *Bs = reinterpret_cast<TileB *>(smem_raw + sizeof(double) * STAGES * BK * SROWA);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp % WM, wn = warp / WM;
+  const double *Ag = A + (size_t)bm * BM_;
   const double *Bg = B + (size_t)bn * BN;
   const int KT = K / BK;
 
   auto load_stage = [&](int stage, int kt) {
     const int k0 = kt * BK;
-    const int mc = (tid & 63) * 2;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int kk = (tid >> 6) + 4 * i;
+    for (int c = tid; c < BK * BM_ / 2; c += 256) {
+      const int kk = c / (BM_ / 2), mc = (c % (BM_ / 2)) * 2;
       cp_async16(&As[stage][kk][mc], Ag + mc + (size_t)(k0 + kk) * lda);
+    }
+#pragma unroll
+    for (int c = tid; c < BK * BN / 2; c += 256) {
+      const int kk = c / (BN / 2), mc = (c % (BN / 2)) * 2;
       cp_async16(&Bs[stage][kk][mc], Bg + mc + (size_t)(k0 + kk) * ldb);
     }
   };
 
-  double acc[8][4][2];
+  double acc[8][NF][2];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NF; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
@@ -93,11 +104,11 @@ k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
       cp_async_commit();
     }
     const int st = kt % STAGES;
-    double a[2][8], b[2][4];
+    double a[2][8], b[2][NF];
 #pragma unroll
     for (int mb = 0; mb < 8; mb++) a[0][mb] = As[st][fk][wm * 64 + mb * 8 + fr];
 #pragma unroll
-    for (int nb = 0; nb < 4; nb++) b[0][nb] = Bs[st][fk][wn * 32 + nb * 8 + fr];
+    for (int nb = 0; nb < NF; nb++) b[0][nb] = Bs[st][fk][wn * (8 * NF) + nb * 8 + fr];
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const int cur = ks & 1, nxt = cur ^ 1;
@@ -105,12 +116,12 @@ k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
 #pragma unroll
         for (int mb = 0; mb < 8; mb++) a[nxt][mb] = As[st][(ks + 1) * 4 + fk][wm * 64 + mb * 8 + fr];
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) b[nxt][nb] = Bs[st][(ks + 1) * 4 + fk][wn * 32 + nb * 8 + fr];
+        for (int nb = 0; nb < NF; nb++) b[nxt][nb] = Bs[st][(ks + 1) * 4 + fk][wn * (8 * NF) + nb * 8 + fr];
       }
 #pragma unroll
       for (int mb = 0; mb < 8; mb++)
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[cur][mb], b[cur][nb]);
+        for (int nb = 0; nb < NF; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[cur][mb], b[cur][nb]);
     }
   }
   cp_async_wait<0>();
@@ -119,10 +130,10 @@ k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
   const bool use_beta = (beta != 0.0);
 #pragma unroll
   for (int mb = 0; mb < 8; mb++) {
-    const int row = bm * BM + wm * 64 + mb * 8 + fr;
+    const int row = bm * BM_ + wm * 64 + mb * 8 + fr;
 #pragma unroll
-    for (int nb = 0; nb < 4; nb++) {
-      const int col = bn * BN + wn * 32 + nb * 8 + 2 * fk;
+    for (int nb = 0; nb < NF; nb++) {
+      const int col = bn * BN + wn * (8 * NF) + nb * 8 + 2 * fk;
       double *c0 = C + row + (size_t)col * ldc;
       double *c1 = c0 + ldc;
       double v0 = alpha * acc[mb][nb][0], v1 = alpha * acc[mb][nb][1];
@@ -133,23 +144,13 @@ k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
 }
 }  // namespace gemm
 
-int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, const double *B, int ldb,
-             double *C, int ldc, double alpha, double beta, bool lower_only) {
-  if (M <= 0 || N <= 0) return 0;
-  if ((M % gemm::BM) || (N % gemm::BN) || (K % gemm::BK) || K <= 0) {
-    fprintf(stderr, "[qpalm_b200] dgemm_nt: bad shape M=%d N=%d K=%d\n", M, N, K);
-    return 1;
-  }
+static int gemm_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)gemm::kSmemBytes));
+    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes<128>()));
+    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes<64>()));
     attr_set = true;
   }
-  dim3 grid(M / gemm::BM, N / gemm::BN);
-  QB_LAUNCH(gemm::k_dgemm_nt, grid, 256, gemm::kSmemBytes, s, K, A, lda, B, ldb, C, ldc, alpha, beta,
-            lower_only ? 1 : 0, 0LL, 0LL, 0LL, (const int *)nullptr, (const int *)nullptr);
-  QB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -157,18 +158,33 @@ int dgemm_nt_batched(cudaStream_t s, int nb, int M, int N, int K, const int *Kz,
                      const double *B, int ldb, long long sB, double *C, int ldc, long long sC, double alpha, double beta,
                      bool lower_only, const int *maskz) {
   if (M <= 0 || N <= 0 || nb <= 0) return 0;
-  if ((M % gemm::BM) || (N % gemm::BN) || (K % gemm::BK)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)gemm::kSmemBytes));
-    attr_set = true;
+  if ((M % gemm::BM) || (N % gemm::BN) || (K % gemm::BK)) {
+    fprintf(stderr, "[qpalm_b200] dgemm_nt: bad shape M=%d N=%d K=%d\n", M, N, K);
+    return 1;
   }
-  dim3 grid(M / gemm::BM, N / gemm::BN, nb);
-  QB_LAUNCH(gemm::k_dgemm_nt, grid, 256, gemm::kSmemBytes, s, K, A, lda, B, ldb, C, ldc, alpha, beta,
-            lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+  if (int e = gemm_attr()) return e;
+  // CTAs that do work with 128-row tiles; below one wave of the GPU the 64-row kernel doubles the parallelism
+  const long long mt = M / gemm::BM, nt = N / gemm::BN;
+  const long long tiles = (lower_only ? (nt <= mt ? nt * mt - nt * (nt - 1) / 2 : mt * (mt + 1) / 2) : mt * nt) * nb;
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; QB_CUDA_TRY(cudaGetDevice(&dev)); QB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  if (tiles < num_sms) {
+    dim3 grid(M / 64, N / gemm::BN, nb);
+    QB_LAUNCH(gemm::k_dgemm_nt<64>, grid, 256, gemm::smem_bytes<64>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+              lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+  } else {
+    dim3 grid(M / gemm::BM, N / gemm::BN, nb);
+    QB_LAUNCH(gemm::k_dgemm_nt<128>, grid, 256, gemm::smem_bytes<128>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+              lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+  }
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+int dgemm_nt(cudaStream_t s, int M, int N, int K, const double *A, int lda, const double *B, int ldb,
+             double *C, int ldc, double alpha, double beta, bool lower_only) {
+  if (K <= 0) { fprintf(stderr, "[qpalm_b200] dgemm_nt: bad shape M=%d N=%d K=%d\n", M, N, K); return 1; }
+  return dgemm_nt_batched(s, 1, M, N, K, nullptr, A, lda, 0, B, ldb, 0, C, ldc, 0, alpha, beta, lower_only, nullptr);
 }
 
 // ================================================================================================
@@ -190,7 +206,6 @@ namespace diag {
 //                    copy of Pt back into As.
 // The inverse X (lower triangular) lives transposed in the upper triangle of As: X(i,c) at As[c*DS + i].
 constexpr int NB = 128, DS = 129, NT = 256, SB = 32, XS = 33, PS = 100;
-constexpr unsigned FULL = 0xffffffffu;
 constexpr size_t kSmemBytes = sizeof(double) * (NB * DS + SB * XS + (NB - SB) * XS + SB * PS + NB) + 16;
 
 using chol32::fstep;
@@ -372,15 +387,15 @@ __device__ __forceinline__ void diag_body(double *Lg, int ld, double *Xg, int *i
   col0 += blockIdx.x * block_stride;
   DIAG_TICK();
 #pragma unroll 1
-  for (int it = 0; it < NB * NB / NT; it += 16) {     // 16 independent loads in flight per thread
-    double t[16];
+  for (int it = 0; it < NB * NB / NT; it += 32) {     // 32 independent loads in flight per thread
+    double t[32];
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
+    for (int q = 0; q < 32; q++) {
       const int idx = tid + (it + q) * NT, i = idx & (NB - 1), k = idx >> 7;
       t[q] = (k <= i) ? Lg[i + (size_t)ld * k] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
+    for (int q = 0; q < 32; q++) {
       const int idx = tid + (it + q) * NT, i = idx & (NB - 1), k = idx >> 7;
       if (k <= i) As[i * DS + k] = t[q];
     }
@@ -480,7 +495,10 @@ int diag_block_phase_clocks(long long *out32) {
 // only inside the current 512-wide outer block.  Everything to the right of the outer block receives ONE
 // rank-512 DMMA update per outer block, which amortises the C-tile read-modify-write of the trailing matrix
 // four times better than rank-128 updates.
-constexpr int kOuter = 512;
+static int outer_block() {   // 512 by default; QPALM_B200_KOUTER=256|1024 for A/B measurements
+  static const int v = [] { const char *e = getenv("QPALM_B200_KOUTER"); const int k = e ? atoi(e) : 512; return (k == 256 || k == 1024) ? k : 512; }();
+  return v;
+}
 
 // Look-ahead (single matrix, npad > 2 * kOuter): the panel chain of an outer block (diagonal-block kernel on one SM,
 // panel solves on npad/128 SMs at most) is latency-bound and leaves most of the GPU idle, while the rank-512 update of
@@ -513,6 +531,7 @@ thread_local LookAhead g_la;
 int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, long long sL, double *invdiag, long long sX,
                         int *info_dev, const int *mask) {
   if (int e = diag_attr()) return e;
+  const int kOuter = outer_block();
   static const bool la_env_off = getenv("QPALM_B200_NO_LOOKAHEAD") != nullptr;
   const bool la = (nb == 1 && !mask && npad > 2 * kOuter && !la_env_off);
   cudaStream_t sc = s;          // stream of the panel chain
@@ -872,9 +891,16 @@ static int chol_solve_flow(cudaStream_t s, int npad, const double *L, int ld, co
   int *flags = st.flags;
   void *args[] = {(void *)&L, (void *)&ld_arg, (void *)&invdiag, (void *)&v, (void *)&nblk_arg, (void *)&flags, (void *)&epoch};
   const bool prof = g_prof_on && prof_begin("flow::k_solve_flow", s);
-  QB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)flow::k_solve_flow, dim3(grid), dim3(flow::NT), args, flow::kSmemBytes, s));
-  ++g_kernel_launches;
+  const cudaError_t err = cudaLaunchCooperativeKernel((const void *)flow::k_solve_flow, dim3(grid), dim3(flow::NT), args, flow::kSmemBytes, s);
   if (prof) prof_end(s);
+  if (err != cudaSuccess) {
+    // e.g. a partitioned GPU (MPS / MIG slice) that cannot co-schedule the grid: remember it and use the per-block launches
+    (void)cudaGetLastError();
+    std::lock_guard<std::mutex> lk(flow::g_flow_mu);
+    flow::g_flow[s].max_grid = -1;
+    return 1;
+  }
+  ++g_kernel_launches;
   return 0;
 }
 
