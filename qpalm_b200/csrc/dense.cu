@@ -508,8 +508,8 @@ static int outer_block() {   // 512 by default; QPALM_B200_KOUTER=256|1024 for A
 // as soon as any SM frees up (an update CTA lasts < 100 us), so the chain is not starved by the queued update.
 namespace {
 struct LookAhead {
-  cudaStream_t hi = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_chain = nullptr, ev_rest = nullptr;
+  cudaStream_t hi = nullptr, mid = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_chain = nullptr, ev_rest = nullptr, ev_panels = nullptr, ev_slabs = nullptr;
   int device = -1;
   int init() {
     int dev = 0;
@@ -518,6 +518,9 @@ struct LookAhead {
     int lo_p = 0, hi_p = 0;
     QB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
     QB_CUDA_TRY(cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hi_p));
+    QB_CUDA_TRY(cudaStreamCreateWithPriority(&mid, cudaStreamNonBlocking, hi_p));
+    QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_panels, cudaEventDisableTiming));
+    QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_slabs, cudaEventDisableTiming));
     QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
     QB_CUDA_TRY(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
@@ -536,11 +539,13 @@ int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, lon
   const bool la = (nb == 1 && !mask && npad > 2 * kOuter && !la_env_off);
   cudaStream_t sc = s;          // stream of the panel chain
   bool rest_pending = false;    // a "rest" update is in flight on s
+  bool slabs_pending = false;   // the update of column slabs 1.. of the current outer block is in flight on g_la.mid
   if (la) {
     if (int e = g_la.init()) return e;
     sc = g_la.hi;
     QB_CUDA_TRY(cudaEventRecord(g_la.ev_in, s));
     QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_in, 0));
+    QB_CUDA_TRY(cudaStreamWaitEvent(g_la.mid, g_la.ev_in, 0));
   }
   for (int J0 = 0; J0 < npad; J0 += kOuter) {
     const int Jend = (J0 + kOuter < npad) ? J0 + kOuter : npad;
@@ -556,10 +561,13 @@ int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, lon
       // rank-128 update of the remaining columns of THIS outer block (all rows below)
       const int wcols = Jend - (j0 + kPanel);
       if (wcols > 0) {
+        // those columns also receive the previous outer block's update from the side stream: wait for it once
+        if (slabs_pending) { QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_slabs, 0)); slabs_pending = false; }
         double *Cin = L + (j0 + kPanel) + (size_t)(j0 + kPanel) * ld;
         if (int e = dgemm_nt_batched(sc, nb, rem, wcols, kPanel, nullptr, L21, ld, sL, L21, ld, sL, Cin, ld, sL, -1.0, 1.0, true, mask)) return e;
       }
     }
+    if (slabs_pending) { QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_slabs, 0)); slabs_pending = false; }
     // rank-(Jend-J0) update of everything to the right of the outer block
     const int rem = npad - Jend;
     if (rem > 0) {
@@ -567,12 +575,22 @@ int potrf_lower_batched(cudaStream_t s, int nb, int npad, double *L, int ld, lon
       double *A22 = L + Jend + (size_t)Jend * ld;
       const int K = Jend - J0;
       if (la && rem > kOuter) {
-        // (a) next outer block's columns, on the chain stream -- after the previous "rest" update, which also wrote them
-        if (rest_pending) QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_rest, 0));
-        if (int e = dgemm_nt_batched(sc, 1, rem, kOuter, K, nullptr, P, ld, 0, P, ld, 0, A22, ld, 0, -1.0, 1.0, true, nullptr)) return e;
-        QB_CUDA_TRY(cudaEventRecord(g_la.ev_chain, sc));
-        // (b) the rest, on the caller's stream, concurrent with the next block's panel chain
-        QB_CUDA_TRY(cudaStreamWaitEvent(s, g_la.ev_chain, 0));
+        // The next outer block's columns first.  Only its FIRST 128-column slab sits on the panel chain; slabs 1.. run on a
+        // second high-priority stream under the next diagonal block + panel solve (they are needed by the first in-block
+        // update only).  Both wait for the previous "rest" update, which wrote the same columns.
+        QB_CUDA_TRY(cudaEventRecord(g_la.ev_panels, sc));
+        if (rest_pending) {
+          QB_CUDA_TRY(cudaStreamWaitEvent(sc, g_la.ev_rest, 0));
+          QB_CUDA_TRY(cudaStreamWaitEvent(g_la.mid, g_la.ev_rest, 0));
+        }
+        if (int e = dgemm_nt_batched(sc, 1, rem, kPanel, K, nullptr, P, ld, 0, P, ld, 0, A22, ld, 0, -1.0, 1.0, true, nullptr)) return e;
+        QB_CUDA_TRY(cudaStreamWaitEvent(g_la.mid, g_la.ev_panels, 0));
+        if (int e = dgemm_nt_batched(g_la.mid, 1, rem - kPanel, kOuter - kPanel, K, nullptr, P + kPanel, ld, 0, P + kPanel, ld, 0,
+                                     A22 + (size_t)kPanel * (ld + 1), ld, 0, -1.0, 1.0, true, nullptr)) return e;
+        QB_CUDA_TRY(cudaEventRecord(g_la.ev_slabs, g_la.mid));
+        slabs_pending = true;
+        // the rest, on the caller's stream, concurrent with the next block's panel chain (needs the finished panels only)
+        QB_CUDA_TRY(cudaStreamWaitEvent(s, g_la.ev_panels, 0));
         const double *P2 = P + kOuter;
         double *A33 = A22 + (size_t)kOuter * (ld + 1);
         if (int e = dgemm_nt_batched(s, 1, rem - kOuter, rem - kOuter, K, nullptr, P2, ld, 0, P2, ld, 0, A33, ld, 0, -1.0, 1.0, true, nullptr)) return e;
