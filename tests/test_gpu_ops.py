@@ -130,9 +130,10 @@ def test_linesearch_all_breakpoints_traversed(gpu_ops, oracle_ops):
 
 
 @pytest.mark.parametrize("n,m,dens,densQ", [(2, 3, 1.0, 1.0), (30, 50, 0.3, 0.2), (128, 64, 0.2, 0.1), (129, 300, 0.1, 0.05),
-                                            (300, 200, 1.0, 1.0), (700, 1500, 0.05, 0.02)])
+                                            (300, 200, 1.0, 1.0), (700, 1500, 0.05, 0.02), (1400, 600, 1.0, 1.0)])
 def test_newton_factor_and_solve(gpu_ops, oracle_ops, n, m, dens, densQ):
-    """(Q + A_J' Sigma_J A_J + beta I) d = rhs through the DMMA SYRK + blocked Cholesky + blocked solves."""
+    """(Q + A_J' Sigma_J A_J + beta I) d = rhs through the DMMA SYRK + blocked Cholesky + blocked solves.
+    n = 1400 (three outer blocks) runs the two-stream look-ahead and both GEMM tile shapes; n > 256 the dataflow solves."""
     p = problems.random_qp(n, m, dens, densQ, seed=21)
     rng = np.random.default_rng(2)
     sigma = 10.0 ** rng.uniform(-1, 2, m)
