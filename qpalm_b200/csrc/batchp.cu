@@ -34,13 +34,18 @@ using namespace qb;
 //                      3 * SMs < nb <= 4 * SMs.
 // Other shapes measured in round 1 (512 instances): 192 threads / PW 24 / 4 per SM 138.6 ms; 192 / PW 16 / 4 per SM
 // 147.7 ms; 256 / PW 16 / 64 regs / 4 per SM 133.0 ms; 192 threads / PW 32 / 3 per SM 192.5 ms (fewer threads per CTA
-// cost more than the extra occupancy buys).
+// cost more than the extra occupancy buys); 4-per-SM shape with 224 threads (72 registers) 142.8 ms, with 288 threads
+// (56 registers) 145.9 ms.
 #ifdef QB_BP_VARIANT4
 #define QB_BP_NAMESPACE bp4
 #define QB_BP_SUPPORTED batchp4_supported
 #define QB_BP_SOLVE batchp4_solve
+#ifndef QB_BP_NT
 #define QB_BP_NT 256
+#endif
+#ifndef QB_BP_PW
 #define QB_BP_PW 24
+#endif
 #define QB_BP_SORT_GLOBAL 1
 #define QB_BP_MINB 4
 #else
