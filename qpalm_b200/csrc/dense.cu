@@ -922,6 +922,15 @@ static int chol_solve_flow(cudaStream_t s, int npad, const double *L, int ld, co
   return 0;
 }
 
+// frees the per-stream flag buffer of the dataflow solves (call before destroying the stream)
+void chol_solve_release(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(flow::g_flow_mu);
+  auto it = flow::g_flow.find(s);
+  if (it == flow::g_flow.end()) return;
+  if (it->second.flags) cudaFree(it->second.flags);
+  flow::g_flow.erase(it);
+}
+
 int chol_solve_batched(cudaStream_t s, int nb, int npad, const double *L, int ld, long long sL, const double *invdiag,
                        long long sX, double *v, long long sV, const int *mask) {
   const int nblk = npad / kPanel;

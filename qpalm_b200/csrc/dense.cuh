@@ -33,6 +33,8 @@ int trtri_diag_blocks(cudaStream_t s, int npad, const double *L, int ld, double 
 
 // v <- (L L')^{-1} v, v of length npad (pad entries must be 0).
 int chol_solve(cudaStream_t s, int npad, const double *L, int ld, const double *invdiag, double *v);
+// releases the per-stream scratch chol_solve keeps (flag buffer of the one-launch dataflow solve); call before destroying s
+void chol_solve_release(cudaStream_t s);
 
 // L <- chol(L L' + sign * W W'), W npad x k (ldw), k <= 8 per call, destroys W.  coef/alpha are scratch
 // (coef: 2 * 32 * 18 doubles, alpha: 8 doubles).  *info_dev set to nonzero if a downdate loses

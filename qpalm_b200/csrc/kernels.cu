@@ -1637,7 +1637,7 @@ void engine_destroy(Engine *e) {
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs0) cudaEventDestroy(e->evs0);
   if (e->evs1) cudaEventDestroy(e->evs1);
-  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->stream) { chol_solve_release(e->stream); cudaStreamDestroy(e->stream); }
   delete e;
 }
 

@@ -473,6 +473,7 @@ extern "C" int qpalm_b200_bench_gemv(c_int n_, c_int m_, c_int reps, double *ms_
   *ms_rows_out = ms / reps;
   cudaEventDestroy(a); cudaEventDestroy(b);
   cudaFree(e.At); cudaFree(e.x); cudaFree(e.y); cudaFree(e.Ax); cudaFree(e.Aty); cudaFree(e.gemv_partials);
+  chol_solve_release(e.stream);
   cudaStreamDestroy(e.stream);
   return 0;
 }
