@@ -436,7 +436,7 @@ def main():
             line["config"]["engine"] = r["stats"]["engine"]
             b0 = r["b"]
             line["roofline"] = batch_roofline(b0.q.shape[1], b0.bmin.shape[1], args.batch, r, steps)
-            if not args.no_cpu:
+            if not args.no_cpu and world == 1:      # the CPU baseline is reported at N = 1 only
                 b = r["b"]
                 count = args.cpu_batch or min(args.batch, cpu_threads())
                 v, cores, kind, cpu_iters = run_cpu_batch_sample(b, count)
@@ -467,7 +467,7 @@ def main():
             line["time_to_solution"] = {"seconds": dev_ms * 1e-3, "e2e_seconds": dense["e2e_s"], "setup_seconds": dense["setup_warm_s"], "setup_seconds_first_call": dense["setup_s"],
                                         "refactorizations": dense["refactorizations"], "updown_sweeps": dense["updown_sweeps"],
                                         "ms_in_refactorizations": dense["ms_factor"], "ms_in_updown": dense["ms_updown"]}
-            if not args.no_cpu:
+            if not args.no_cpu and world == 1:
                 dt, rr, kind = run_cpu_dense_sample(args.cpu_n, 2 * args.cpu_n, args.seed)
                 line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "solves/s", "cores": cpu_threads(), "kind": kind,
                                         "sample": f"same generator at n={args.cpu_n}, m={2 * args.cpu_n} (setup+solve {dt:.2f} s, "
