@@ -143,3 +143,17 @@ def test_qps_solve_matches_reference_solve(tmp_path):
     assert np.max(np.abs(x - ref.x)) / max(1.0, np.max(np.abs(ref.x))) < 1e-8
     assert np.max(np.abs(y - ref.y)) / max(1.0, np.max(np.abs(ref.y))) < 1e-8
     assert abs(info["iter"] - ref.iter) <= max(1, ref.iter // 20)
+
+
+def test_reader_extensions_beyond_the_reference(tmp_path):
+    """Inputs the reference reader does not accept: comment lines, an OBJSENSE section, QMATRIX (full symmetric listing:
+    only the lower triangle is kept, as QUADOBJ would have given) and RHS / BOUNDS without set names mixed with comments."""
+    f = tmp_path / "ext.qps"
+    f.write_text(
+        "NAME EXT\n* a comment\nOBJSENSE\n    MIN\nROWS\n N obj\n G r1\nCOLUMNS\n    x obj 1.0 r1 1.0\n    y obj 2.0 r1 1.0\n"
+        "RHS\n    r1 1.0\n* another comment\nBOUNDS\n UP x 3.0\n PL y\nQMATRIX\n    x x 2.0\n    x y -1.0\n    y x -1.0\n    y y 4.0\nENDATA\n")
+    p = qps.read_qps(str(f))
+    assert (p.n, p.m) == (2, 3)
+    assert p.Q_p.tolist() == [0, 2, 3] and p.Q_i.tolist() == [0, 1, 1] and p.Q_x.tolist() == [2.0, -1.0, 4.0]
+    assert p.bmin.tolist() == [1.0, 0.0, 0.0] and p.bmax.tolist() == [1e20, 3.0, 1e20]
+    assert p.A_i.tolist() == [0, 1, 0, 2]
