@@ -378,9 +378,10 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
   }
 }
 
-// Refactor-vs-update cost model (DESIGN.md): the rank-k sweep is a chain of npad/32 dependent panel steps
-// (~30 us + ~12 us per rank each, measured on B200), a refactorisation is DMMA-bound; the update path is taken
-// only when it is predicted to be cheaper than the last measured refactorisation.  Same matrix either way.
+// Refactor-vs-update cost model (DESIGN.md section 4): the rank-k sweep is a chain of npad/32 dependent panel steps
+// (~83 us each at n = 8000, measured on B200), a refactorisation is a panel chain plus DMMA-bound updates.  Dense
+// factor: a static model, so the choice never depends on timing; sparse factor: the measured time of the last sweep
+// against the last refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0 || k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->sh_world > 1) return false;   // row-sharded: the entering rows live on different ranks; refactorise (allreduced H)
