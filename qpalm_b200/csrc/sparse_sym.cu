@@ -13,6 +13,7 @@
 #include "sparse_host.h"
 
 #include <algorithm>
+#include <chrono>
 #include <set>
 #include <tuple>
 #include <stdio.h>
@@ -38,14 +39,42 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
     if (tie_mode == 3) return (long long)((unsigned)(i * 2654435761u) >> 4);
     return 0;
   };
+  // Priority structure.  Default tie rule (most recently updated first) = degree buckets with LIFO insertion, O(1) per
+  // operation: the same order as the (degree, -stamp) keys of the ordered set, which stays as the fallback for the
+  // experimental tie rules (the set cost 2 log n per updated variable: 1.2 s of the 1.3 s analysis at n = 90 000).
+  const bool buckets = (tie_mode == 1);
+  std::vector<int> bhead, bnext, bprev;
+  int mindeg = 0;
+  auto b_insert = [&](int i, int d) {
+    bnext[i] = bhead[d]; bprev[i] = -1;
+    if (bhead[d] != -1) bprev[bhead[d]] = i;
+    bhead[d] = i;
+    if (d < mindeg) mindeg = d;
+  };
+  auto b_remove = [&](int i, int d) {
+    if (bprev[i] != -1) bnext[bprev[i]] = bnext[i]; else bhead[d] = bnext[i];
+    if (bnext[i] != -1) bprev[bnext[i]] = bprev[i];
+  };
   std::set<std::tuple<int, long long, int>> heap;
-  for (int i = 0; i < n; i++) { degree[i] = (int)vadj[i].size(); tkey[i] = tie(i); heap.insert({degree[i], tkey[i], i}); }
+  if (buckets) { bhead.assign(n + 1, -1); bnext.assign(n, -1); bprev.assign(n, -1); mindeg = n; }
+  for (int i = 0; i < n; i++) {
+    degree[i] = (int)vadj[i].size();
+    if (buckets) b_insert(i, degree[i]);
+    else { tkey[i] = tie(i); heap.insert({degree[i], tkey[i], i}); }
+  }
   order.clear(); order.reserve(n);
   int wbase = 1;
   std::vector<int> Lp;
   for (int k = 0; k < n; k++) {
-    const int p = std::get<2>(*heap.begin());
-    heap.erase(heap.begin());
+    int p;
+    if (buckets) {
+      while (bhead[mindeg] == -1) mindeg++;
+      p = bhead[mindeg];
+      b_remove(p, mindeg);
+    } else {
+      p = std::get<2>(*heap.begin());
+      heap.erase(heap.begin());
+    }
     order.push_back(p);
     // ---- form the new element L_p ----
     Lp.clear();
@@ -69,7 +98,7 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
     // ---- prune the adjacency of the members, update their degrees ----
     const int lp = (int)Lp.size();
     for (int i : Lp) {
-      heap.erase({degree[i], tkey[i], i});
+      if (buckets) b_remove(i, degree[i]); else heap.erase({degree[i], tkey[i], i});
       size_t o = 0;
       for (int v : vadj[i]) if (state[v] == 0 && mark[v] != k) vadj[i][o++] = v;   // drop p, members of L_p, eliminated
       vadj[i].resize(o);
@@ -89,8 +118,8 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
       if (d > n - k - 2) d = n - k - 2;
       if (d < 0) d = 0;
       degree[i] = (int)d;
-      tkey[i] = tie(i);
-      heap.insert({degree[i], tkey[i], i});
+      if (buckets) b_insert(i, degree[i]);
+      else { tkey[i] = tie(i); heap.insert({degree[i], tkey[i], i}); }
     }
     // an element absorbed above (L_e inside L_p) is referenced by no variable any more: all its variables are in L_p and
     // each of them just dropped it; it simply becomes unreachable
@@ -104,6 +133,14 @@ static void min_degree_order(int n, const std::vector<std::vector<int>> &adj, st
 int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const int *Acsr_p, const int *Acsr_j,
                      const long long *Qp, const long long *Qi, bool force, SymHost *S) {
   S->n = n;
+  const bool timing = getenv("QPALM_B200_SYM_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[qpalm_b200] symbolic: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   // ---- union pattern (full symmetric adjacency without the diagonal) ----
   const double cap = force ? 4.0e18 : 0.12 * (double)n * (double)n + 64.0 * n;
   std::vector<std::vector<int>> adj(n);
@@ -130,9 +167,11 @@ int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const i
     }
     S->nnzS = (long long)(total / 2) + n;
   }
+  lap("union pattern");
   // ---- fill-reducing ordering ----
   std::vector<int> order;
   min_degree_order(n, adj, order);
+  lap("minimum-degree ordering");
   std::vector<int> iperm(n);
   for (int k = 0; k < n; k++) iperm[order[k]] = k;
   // ---- elimination tree of the permuted pattern ----
@@ -175,6 +214,7 @@ int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const i
     parent.swap(np);
     for (int v = 0; v < n; v++) iperm[v] = post[iperm[v]];
   }
+  lap("etree + postorder");
   S->iperm = iperm;
   S->perm.assign(n, 0);
   for (int v = 0; v < n; v++) S->perm[iperm[v]] = v;
@@ -207,6 +247,7 @@ int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const i
         if (j == fs_first[s] && i >= fs_first[s + 1]) rows[s].push_back(i);
       }
   }
+  lap("counts + row structure");
   // ---- relaxed amalgamation: a supernode may absorb the supernode immediately before it when that one is its child ----
   std::vector<int> first(fs_first.begin(), fs_first.end() - 1), ncol(nfs);
   std::vector<double> zeros(nfs, 0.0);
@@ -293,6 +334,7 @@ int symbolic_analyze(int n, int m, const int *Acsc_p, const int *Acsc_i, const i
     std::vector<int> fill(S->lvl_ptr.begin(), S->lvl_ptr.end() - 1);
     for (int t = 0; t < ns_; t++) S->lvl_sn[fill[level[t]]++] = t;
   }
+  lap("supernodes + assembly tree");
   S->lvl_max_ns.assign(nl, 0); S->lvl_max_nf.assign(nl, 0); S->lvl_max_child_nr.assign(nl, 0);
   for (int t = 0; t < ns_; t++) {
     const int ns = S->sn_first[t + 1] - S->sn_first[t], nf = ns + S->rows_off[t + 1] - S->rows_off[t];
