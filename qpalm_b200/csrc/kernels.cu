@@ -6,6 +6,7 @@
 // are bit-identical to the reference at identical inputs.
 #include "engine.cuh"
 #include <vector>
+#include <chrono>
 #include <math.h>
 #include <string.h>
 
@@ -1442,6 +1443,15 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   QB_CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (ndev <= 0) { fprintf(stderr, "[qpalm_b200] no CUDA device: this library has no CPU fallback\n"); return 1; }
   Engine *e = new Engine();
+  const bool timing = getenv("QPALM_B200_SETUP_TIMING") != nullptr;   // phase timers of the setup path (stderr)
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[qpalm_b200] setup: %-32s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   QB_CUDA_TRY(cudaGetDevice(&e->device));
   // a BLOCKING stream: setup uses cudaMemset/cudaMemcpy on the legacy default stream, which must stay ordered
   // with the kernels of this engine (a non-blocking stream raced with the allocation memsets)
@@ -1498,6 +1508,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     hA_cp.assign(cp, cp + n + 1); hA_ci.assign(ci, ci + nnzA); hA_rp.assign(rp + 0, rp + m + 1); hA_rj.assign(rj, rj + nnzA);
     free(cp); free(ci); free(rp); free(rj); free(rx);
   }
+  lap("A: convert + upload");
   // ---- Q (only row >= col entries are read: stype -1) ----
   long long nnzL = 0;
   for (int j = 0; j < n; j++) for (long long k = Qp[j]; k < Qp[j + 1]; k++) if (Qi[k] >= j) nnzL++;
@@ -1535,6 +1546,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     if (int r = upload_sparse(&e->Q_csr, n, n, start, rj, rx)) return r;
     free(cnt); free(start); free(fill); free(rj); free(rx);
   }
+  lap("Q: convert + upload");
   // ---- vectors ----
   const size_t N = (size_t)n, M = (size_t)(e->sh_world > 1 ? e->sh_world * e->m_cap : m);   // m-vectors padded for the in-place allgather
   auto dv = [&](double **p, size_t len) { return dev_alloc((void **)p, sizeof(double) * (len ? len : 1)); };
@@ -1561,6 +1573,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   e->rs_tiles = cdiv((int)(2 * M) > 0 ? (int)(2 * M) : 1, rsort::TILE);
   rc |= dev_alloc((void **)&e->rs_hist, sizeof(unsigned int) * 256 * (size_t)e->rs_tiles);
   if (rc) return rc;
+  lap("vectors");
   // ---- Newton system ----
   // sparse problems whose Schur complement Q + A'A stays sparse: supernodal factor (sparse.cu) instead of dense H / L.
   {
@@ -1576,6 +1589,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
       }
     }
   }
+  lap("sparse symbolic analysis + upload");
   const size_t LL = e->sp ? 1 : (size_t)e->ld * e->npad;
   size_t free_b = 0, total_b = 0;
   QB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -1615,6 +1629,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   if (const char *s = getenv("QPALM_B200_UPDOWN_MAX_RANK")) e->updown_max_rank = atoi(s);
   if (const char *s = getenv("QPALM_B200_UPDOWN_FORCE")) e->updown_force = atoi(s);
   QB_CUDA_TRY(cudaDeviceSynchronize());
+  lap("factor storage + scratch");
   *out = e;
   return 0;
 }
