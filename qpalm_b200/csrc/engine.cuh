@@ -51,6 +51,10 @@ struct SparseDev {           // CSR or CSC, int32 indices
 struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // one zero-filled slab for the ~80 iterate / work vectors (a cudaMalloc + cudaMemset per vector cost 113 ms of the
+  // setup at m = 359k); buffers carved from it are not freed individually
+  char *arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
   int n = 0, m = 0, npad = 0, ld = 0;
   bool A_dense = false, Q_dense = false;
   // row-sharding (shard.cu): this rank holds constraint rows [m_lo, m_lo + m_loc) of A in `At` (n x m_loc); vectors of

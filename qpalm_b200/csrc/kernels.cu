@@ -29,6 +29,16 @@ int dev_alloc(void **p, size_t bytes) {
   QB_CUDA_TRY(cudaMemset(*p, 0, bytes));
   return 0;
 }
+// carve from the engine's zero-filled slab; falls back to an individual allocation when the slab is exhausted
+static int arena_alloc(Engine *e, void **p, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (e->arena && e->arena_off + need <= e->arena_cap) { *p = e->arena + e->arena_off; e->arena_off += need; return 0; }
+  return dev_alloc(p, bytes);
+}
+static bool in_arena(const Engine *e, const void *p) {
+  return e->arena && (const char *)p >= e->arena && (const char *)p < e->arena + e->arena_cap;
+}
 int upload(Engine *e, double *dst, const double *src, int len) {
   if (len > 0) QB_CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, e->stream));
   return 0;
@@ -1549,8 +1559,15 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   lap("Q: convert + upload");
   // ---- vectors ----
   const size_t N = (size_t)n, M = (size_t)(e->sh_world > 1 ? e->sh_world * e->m_cap : m);   // m-vectors padded for the in-place allgather
-  auto dv = [&](double **p, size_t len) { return dev_alloc((void **)p, sizeof(double) * (len ? len : 1)); };
-  auto iv = [&](int **p, size_t len) { return dev_alloc((void **)p, sizeof(int) * (len ? len : 1)); };
+  {   // slab for everything allocated through dv / iv / the sort buffers below (sizes: 40 m-, 24 n-, 8 2m-vectors + slack)
+    const size_t cap = 8 * (40 * M + 24 * N + 8 * (2 * M + 1) + (size_t)e->npad) + 4 * 12 * M + 256 * 128 + (1u << 20);
+    if (cudaMalloc((void **)&e->arena, cap) == cudaSuccess) {
+      e->arena_cap = cap; e->arena_off = 0;
+      QB_CUDA_TRY(cudaMemset(e->arena, 0, cap));
+    } else { (void)cudaGetLastError(); e->arena = nullptr; }
+  }
+  auto dv = [&](double **p, size_t len) { return arena_alloc(e, (void **)p, sizeof(double) * (len ? len : 1)); };
+  auto iv = [&](int **p, size_t len) { return arena_alloc(e, (void **)p, sizeof(int) * (len ? len : 1)); };
   int rc = 0;
   rc |= up(&e->q, q, N); rc |= dv(&e->bmin, M); rc |= dv(&e->bmax, M);
   if (!rc && m > 0) { rc |= upload(e, e->bmin, bmin, m); rc |= upload(e, e->bmax, bmax, m); }
@@ -1565,10 +1582,10 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   rc |= iv(&e->active, M); rc |= iv(&e->active_old, M); rc |= iv(&e->active_cand, M); rc |= iv(&e->enter, M); rc |= iv(&e->leave, M);
   rc |= iv(&e->changed, M); rc |= iv(&e->list_pos, M); rc |= iv(&e->list_neg, M); rc |= dv(&e->w_pos, M); rc |= dv(&e->w_neg, M);
   rc |= iv(&e->activeH, M); rc |= dv(&e->sigmaH, M);
-  rc |= dev_alloc((void **)&e->ls_key[0], sizeof(unsigned long long) * (2 * M + 1));
-  rc |= dev_alloc((void **)&e->ls_key[1], sizeof(unsigned long long) * (2 * M + 1));
-  rc |= dev_alloc((void **)&e->ls_val[0], sizeof(unsigned int) * (2 * M + 1));
-  rc |= dev_alloc((void **)&e->ls_val[1], sizeof(unsigned int) * (2 * M + 1));
+  rc |= arena_alloc(e, (void **)&e->ls_key[0], sizeof(unsigned long long) * (2 * M + 1));
+  rc |= arena_alloc(e, (void **)&e->ls_key[1], sizeof(unsigned long long) * (2 * M + 1));
+  rc |= arena_alloc(e, (void **)&e->ls_val[0], sizeof(unsigned int) * (2 * M + 1));
+  rc |= arena_alloc(e, (void **)&e->ls_val[1], sizeof(unsigned int) * (2 * M + 1));
   rc |= dv(&e->ls_da, 2 * M); rc |= dv(&e->ls_db, 2 * M);
   e->rs_tiles = cdiv((int)(2 * M) > 0 ? (int)(2 * M) : 1, rsort::TILE);
   rc |= dev_alloc((void **)&e->rs_hist, sizeof(unsigned int) * 256 * (size_t)e->rs_tiles);
@@ -1645,7 +1662,8 @@ void engine_destroy(Engine *e) {
                   e->list_pos, e->list_neg, e->w_pos, e->w_neg, e->activeH, e->sigmaH, e->ls_key[0], e->ls_key[1],
                   e->ls_val[0], e->ls_val[1], e->ls_da, e->ls_db, e->rs_hist, e->H, e->L, e->invdiag, e->W, e->LQ,
                   e->invdiagQ, e->ud_coef, e->partials, e->gemv_partials, e->scal_dev, e->info_dev, e->spL, e->spLQ};
-  for (void *p : ptrs) if (p) cudaFree(p);
+  for (void *p : ptrs) if (p && !in_arena(e, p)) cudaFree(p);
+  if (e->arena) cudaFree(e->arena);
   sparse_chol_destroy(e->sp);
   if (e->scal_host) cudaFreeHost(e->scal_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
