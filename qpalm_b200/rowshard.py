@@ -32,3 +32,13 @@ def init(rank: int, world: int, device=None) -> None:
 
 def finalize() -> None:
     load_library("b200").qpalm_b200_shard_finalize()
+
+
+def row_block(m: int, rank: int, world: int):
+    """Constraint rows [lo, lo + cnt) kept by `rank`, and the padded block size `cap` of the in-place allgather --
+    the partition engine_create (csrc/kernels.cu) applies when qpalm_b200_shard_init was called: equal blocks of
+    cap = ceil(m / world) rows, the last ranks possibly short or empty."""
+    cap = -(-m // world)
+    lo = min(rank * cap, m)
+    cnt = max(0, min(cap, m - rank * cap))
+    return lo, cnt, cap
