@@ -104,7 +104,8 @@ def get_stats(lib, solver) -> abi.QPALMB200Stats:
 # reference / oracle CPU arm
 # ------------------------------------------------------------------------------------------------------
 def cpu_impl():
-    return ("reference", "reference") if os.path.exists(abi.REF_LIB) else ("oracle", "port")
+    from oracle import refbind   # the checker libraries: cpu_baseline / --impl reference legs only
+    return ("reference", "reference") if refbind.have_reference() else ("oracle", "port")
 
 
 def cpu_threads():

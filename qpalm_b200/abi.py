@@ -1,10 +1,7 @@
 """ctypes mirror of include/qpalm_b200.h (Part 1) -- the drop-in ABI.
 
-The same struct layouts describe three shared libraries:
-
-* ``qpalm_b200/libqpalm_b200.so``   the product (CUDA, sm_100a),
-* ``oracle/_ref/libqpalm_ref.so``   the unmodified reference (CHOLMOD build), test infrastructure,
-* ``oracle/liboracle.so``           the plain-C restatement, test infrastructure (``oracle_`` prefix).
+The struct layouts are the reference's, so the same classes describe ``qpalm_b200/libqpalm_b200.so`` (the product,
+CUDA, sm_100a) and any other library exporting the reference API (the test infrastructure binds two, oracle/refbind.py).
 
 Reference for the layouts: /root/reference/include/types.h:37-314 and the field-by-field ctypes
 mirror in /root/reference/interfaces/python/qpalm.py:15-190.
@@ -23,8 +20,6 @@ c_float_p = C.POINTER(c_float)
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_LIB = os.environ.get("QPALM_B200_LIB") or os.path.join(REPO_ROOT, "qpalm_b200", "libqpalm_b200.so")   # override: A/B builds
-REF_LIB = os.path.join(REPO_ROOT, "oracle", "_ref", "libqpalm_ref.so")
-ORACLE_LIB = os.path.join(REPO_ROOT, "oracle", "liboracle.so")
 
 QPALM_SOLVED = 1
 QPALM_DUAL_TERMINATED = 2

@@ -3,12 +3,13 @@
 ``Qpalm`` keeps the reference class's method names (``set_data``, ``_solve``, ``_warm_start``,
 ``_update_bounds``, ``_update_q``, ``_update_settings``) and argument meaning, but talks to the
 drop-in C ABI of this repository directly (no ``python_allocate_*`` helper library is needed because
-the structs are built with ctypes).  ``impl`` selects which shared library is bound:
+the structs are built with ctypes).  ``impl="b200"`` binds qpalm_b200/libqpalm_b200.so -- the product.
+Loading fails loudly if the CUDA library has not been built; there is no CPU fallback.
 
-* ``"b200"``       qpalm_b200/libqpalm_b200.so -- the product.  Loading fails loudly if the CUDA
-                   library has not been built; there is no CPU fallback.
-* ``"reference"``  oracle/_ref/libqpalm_ref.so -- test/bench infrastructure only.
-* ``"oracle"``     oracle/liboracle.so (``oracle_`` symbol prefix) -- test infrastructure only.
+The class is generic over any library that exports the reference API, so the test infrastructure
+(oracle/refbind.py, which this package never imports) can register the compiled reference and the CPU
+oracle as extra ``impl`` names through ``register_checker`` and drive them with the same code the tests
+use on the product.
 """
 from __future__ import annotations
 
@@ -24,33 +25,33 @@ from .abi import (CSC, QPALMData, QPALMInfo, QPALMSettings, QPALMWorkspace, c_fl
 _LIBS: dict[str, C.CDLL] = {}
 
 
-def _preload_blas():
-    """The reference oracle links the OpenBLAS bundled in the opencv wheel (oracle/Makefile); that
-    library needs its sibling libgfortran/libquadmath, which are not on the loader path."""
-    import glob
-    import sysconfig
-    d = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
-    for pat in ("libquadmath*", "libgfortran*", "libopenblasp*"):
-        for f in sorted(glob.glob(os.path.join(d, pat))):
-            try:
-                C.CDLL(f, mode=os.RTLD_GLOBAL | os.RTLD_NOW)
-            except OSError:
-                pass
+_CHECKERS: dict[str, tuple] = {}
+
+
+def register_checker(impl: str, path: str, prefix: str, loader) -> None:
+    """Called by oracle/refbind.py (test infrastructure) only: makes ``Qpalm(impl)`` bind another library that exports the
+    reference API (symbol prefix ``prefix``).  The product never registers anything."""
+    if impl == "b200":
+        raise ValueError("the product library cannot be re-bound")
+    _CHECKERS[impl] = (path, prefix, loader)
 
 
 def load_library(impl: str = "b200") -> C.CDLL:
-    """Load (once) and type one of the three libraries."""
+    """Load (once) and type the product library (or a checker library registered by the test infrastructure)."""
     if impl in _LIBS:
         return _LIBS[impl]
-    path = {"b200": abi.PRODUCT_LIB, "reference": abi.REF_LIB, "oracle": abi.ORACLE_LIB}[impl]
+    if impl == "b200":
+        path, pre, loader = abi.PRODUCT_LIB, "", None
+    elif impl in _CHECKERS:
+        path, pre, loader = _CHECKERS[impl]
+    else:
+        raise RuntimeError(f"unknown implementation {impl!r}: the product binds \"b200\" only (checker libraries are "
+                           "registered by the test infrastructure, oracle/refbind.py)")
     if not os.path.exists(path):
         raise RuntimeError(
             f"{impl}: shared library {path} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`"
             + (" (the product has no CPU fallback)" if impl == "b200" else ""))
-    if impl == "reference":
-        _preload_blas()
-    lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
-    pre = "oracle_" if impl == "oracle" else ""
+    lib = loader() if loader else C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
     W = C.POINTER(QPALMWorkspace)
 
     def sym(name):

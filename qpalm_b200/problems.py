@@ -171,7 +171,13 @@ def random_qp(n, m, dens_A=0.05, dens_M=0.007, seed=0, nonconvex_shift=0.0, name
                                      data_rvs=rng.standard_normal))
     if dens_M >= 1.0:
         M = rng.standard_normal((n, n))
-        Qd = _gram(M)
+        if n >= 2000:
+            # BASELINE-sized dense instances: M is rounded to a 2^-10 grid, so every product and partial sum of
+            # M M' is an integer below 2^53 and Q comes out bit-identical under any BLAS / GPU / summation order.
+            # The committed reference records (tests/golden/*_n8000*) are therefore valid on every machine.
+            Qd = _gram(np.round(M * 1024.0)) / 1048576.0
+        else:
+            Qd = _gram(M)
         if nonconvex_shift:
             Qd[np.diag_indices(n)] -= nonconvex_shift
         Q = CSC.from_dense(Qd, stype=-1)

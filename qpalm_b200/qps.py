@@ -3,7 +3,6 @@
 ``read_qps``       -> qpalm_b200_qps_read       (get_sizes_and_check_format + read_data, qpalm_qps.c:69-575)
 ``read_settings``  -> qpalm_b200_read_settings  (read_settings, qpalm_qps.c:610-689)
 ``solve_qps``      -> qpalm_b200_qps_solve      (main, qpalm_qps.c:692-831): read, upload, solve on the GPU
-``read_qps_reference`` drives the unmodified reference reader (oracle/_ref/libqpalm_qps_ref.so, test infrastructure).
 ``write_qps`` writes a problem in the free QPS format the Maros-Meszaros set uses -- the reference has no writer; the
 tests and ``bench.py`` use it to make synthetic stand-ins for the absent .qps files (SURVEY.md 8(c) "data not available").
 """
@@ -17,9 +16,7 @@ import numpy as np
 
 from . import abi
 from .abi import QPALMData, QPALMInfo, QPALMSettings
-from .interface import load_library, _preload_blas
-
-REF_QPS_LIB = os.path.join(abi.REPO_ROOT, "oracle", "_ref", "libqpalm_qps_ref.so")
+from .interface import load_library
 
 
 @dataclass
@@ -115,43 +112,6 @@ def solve_qps(path: str, settings_path: str | None = None):
     return ({"status": info.status.decode(), "status_val": int(info.status_val), "iter": int(info.iter),
              "iter_out": int(info.iter_out), "objective": float(info.objective), "solve_time": float(info.solve_time),
              "setup_time": float(info.setup_time)}, x, y)
-
-
-# ---------------------------------------------------------------------------------------------
-# test infrastructure: the unmodified reference reader
-# ---------------------------------------------------------------------------------------------
-_REF = None
-
-
-def reference_reader_available() -> bool:
-    return os.path.exists(REF_QPS_LIB) and os.path.exists(abi.REF_LIB)
-
-
-def _ref():
-    global _REF
-    if _REF is None:
-        _preload_blas()
-        C.CDLL(abi.REF_LIB, mode=os.RTLD_GLOBAL | os.RTLD_NOW)
-        lib = C.CDLL(REF_QPS_LIB, mode=os.RTLD_LOCAL | os.RTLD_NOW)
-        lib.qps_ref_read.argtypes = [C.c_char_p]
-        lib.qps_ref_read.restype = C.POINTER(QPALMData)
-        lib.qps_ref_read_settings.argtypes = [C.c_char_p, C.POINTER(QPALMSettings)]
-        lib.qps_ref_read_settings.restype = None
-        _REF = lib
-    return _REF
-
-
-def read_qps_reference(path: str) -> QPSProblem:
-    d = _ref().qps_ref_read(os.fsencode(path))
-    if not d:
-        raise RuntimeError(f"reference reader failed on {path}")
-    return _unpack(d.contents, "")          # the few reference-owned buffers are left to the process
-
-
-def read_settings_reference(path: str) -> dict:
-    s = QPALMSettings()
-    _ref().qps_ref_read_settings(os.fsencode(path), C.byref(s))
-    return {f: getattr(s, f) for f, _ in QPALMSettings._fields_}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from qpalm_b200 import abi  # noqa: E402
+from oracle import refbind  # noqa: E402  (registers the "oracle" / "reference" checker libraries)
 from qpalm_b200.interface import load_library  # noqa: E402
 
 
@@ -26,7 +27,7 @@ def _has_gpu():
 
 
 HAS_GPU = _has_gpu()
-HAS_REF = os.path.exists(abi.REF_LIB)
+HAS_REF = refbind.have_reference()
 
 
 class Ops:

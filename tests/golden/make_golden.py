@@ -16,7 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from qpalm_b200 import problems  # noqa: E402
-from qpalm_b200.interface import Qpalm  # noqa: E402
+from oracle.refbind import Qpalm  # noqa: E402
 
 libc = ctypes.CDLL("libc.so.6")
 

@@ -15,6 +15,7 @@ import scipy.sparse as sp
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from qpalm_b200 import qps  # noqa: E402
+from oracle import refbind  # noqa: E402
 
 INF = 1e20
 
@@ -47,10 +48,10 @@ def main():
     for path in sorted(glob.glob(os.path.join(HERE, "qps", "*.qps"))):
         if os.path.basename(path).startswith("mine_"):
             continue                      # inputs the reference reader cannot handle (see tests/test_qps.py)
-        p = qps.read_qps_reference(path)
+        p = refbind.read_qps_reference(path)
         out[os.path.basename(path)] = {k: (getattr(p, k).tolist() if hasattr(getattr(p, k), "tolist") else getattr(p, k))
                                        for k in ("n", "m", "A_p", "A_i", "A_x", "Q_p", "Q_i", "Q_x", "q", "c", "bmin", "bmax")}
-    out["qps_settings.txt"] = qps.read_settings_reference(os.path.join(HERE, "qps_settings.txt"))
+    out["qps_settings.txt"] = refbind.read_settings_reference(os.path.join(HERE, "qps_settings.txt"))
     with open(os.path.join(HERE, "qps_ref_outputs.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote", len(out), "entries")

@@ -105,3 +105,22 @@ def test_default_settings_match_reference_constants():
     d = abi.default_settings_py()
     for name, _ in abi.QPALMSettings._fields_:
         assert getattr(s, name) == getattr(d, name), name
+
+
+def test_product_package_never_touches_the_checkers():
+    """The oracle / compiled reference are test infrastructure: no module of qpalm_b200/ may import, load or name them, and a
+    fresh interpreter that imports the whole product package must know only the "b200" implementation."""
+    import glob
+    import subprocess
+    import sys
+    pkg = os.path.join(abi.REPO_ROOT, "qpalm_b200")
+    for f in glob.glob(os.path.join(pkg, "*.py")):
+        src = open(f).read()
+        for bad in ("import oracle", "from oracle", "liboracle", "libqpalm_ref", "libqpalm_qps_ref", "oracle/_ref"):
+            assert bad not in src, (f, bad)
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import qpalm_b200.interface as i, qpalm_b200.qps, qpalm_b200.batch, qpalm_b200.sparse, qpalm_b200.mpc\n"
+            "assert not i._CHECKERS and 'oracle' not in sys.modules and 'oracle.refbind' not in sys.modules\n"
+            "try:\n    i.load_library('oracle')\nexcept RuntimeError as e:\n    print('refused:', str(e)[:40])\n" % abi.REPO_ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "refused" in out.stdout, out.stderr

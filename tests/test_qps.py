@@ -16,6 +16,7 @@ import pytest
 import scipy.sparse as sp
 
 from qpalm_b200 import problems, qps
+from oracle import refbind
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
@@ -112,12 +113,12 @@ def _random_problem_file(tmp_path, seed, n, m0, **kw):
     return path
 
 
-@pytest.mark.skipif(not qps.reference_reader_available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.skipif(not refbind.reference_reader_available(), reason="oracle/_ref not built (no /root/reference here)")
 @pytest.mark.parametrize("seed,n,m0,kw", [(0, 30, 20, {}), (1, 200, 150, dict(rhs_name=None, bnd_name=None)),
                                           (2, 64, 1, dict(two_per_line=False)), (3, 500, 700, {})])
 def test_reader_matches_live_reference(tmp_path, seed, n, m0, kw):
     path = _random_problem_file(tmp_path, seed, n, m0, **kw)
-    _same(qps.read_qps(path), qps.read_qps_reference(path))
+    _same(qps.read_qps(path), refbind.read_qps_reference(path))
 
 
 @pytest.mark.gpu
@@ -136,7 +137,7 @@ def test_qps_solve_matches_reference_solve(tmp_path):
     st.write_text("#\n#\n#\n#\n#\neps_abs 1e-6\neps_rel 1e-6\nverbose 0\n")
     info, x, y = qps.solve_qps(path, str(st))
     p = qps.read_qps(path)
-    ref = solve_qp("reference" if os.path.exists(qps.abi.REF_LIB) else "oracle",
+    ref = solve_qp("reference" if refbind.have_reference() else "oracle",
                    CSC(n, n, p.Q_p, p.Q_i, p.Q_x, -1), CSC(p.m, n, p.A_p, p.A_i, p.A_x, 0), p.q, p.bmin, p.bmax, c=p.c,
                    eps_abs=1e-6, eps_rel=1e-6, verbose=0)
     assert info["status_val"] == ref.status_val == 1

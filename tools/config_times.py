@@ -11,6 +11,7 @@ import ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import scipy.sparse as sp
+import oracle.refbind  # noqa: F401  (registers the "reference" / "oracle" checker libraries)
 from qpalm_b200 import problems, qps
 from qpalm_b200.interface import Qpalm, solve_qp
 from qpalm_b200.problems import CSC

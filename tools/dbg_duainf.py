@@ -1,5 +1,6 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle.refbind  # noqa: F401  (registers the "reference" / "oracle" checker libraries)
 from qpalm_b200 import problems
 from qpalm_b200.interface import solve_qp
 p = problems.dua_inf_qp()

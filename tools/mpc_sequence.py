@@ -2,6 +2,7 @@
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import oracle.refbind  # noqa: F401  (registers the "reference" / "oracle" checker libraries)
 from qpalm_b200 import mpc
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 b, seq = mpc.mpc_sequence(steps, seed=1)

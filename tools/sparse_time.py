@@ -7,6 +7,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import oracle.refbind  # noqa: F401  (registers the "reference" / "oracle" checker libraries)
 from qpalm_b200 import abi, problems
 from qpalm_b200.interface import Qpalm, load_library, solve_qp
 
