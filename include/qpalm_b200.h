@@ -209,6 +209,8 @@ typedef struct {
   int64_t sparse_factor_nnz;    /* entries of the supernodal factor (0: the dense Newton path is in use)  */
   int64_t sparse_supernodes;
   int64_t sparse_levels;        /* assembly-tree levels = launches-in-sequence of one factorization pass */
+  int64_t sigma_update_calls;   /* ldlupdate_sigma_changed equivalents taken (rank updates after a sigma change) */
+  int64_t sigma_update_rank_sum;
 } QPALMB200Stats;
 int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *out);
 /* Selective per-kernel CUDA-event timing of the library's own launches (csrc/prof.cu): `patterns` is a comma-separated
@@ -289,6 +291,8 @@ int qpalm_b200_lobpcg(const solver_sparse *Q, const c_float *x0, c_float *lambda
  * C(n x n lower) = W W' with W n x k; returns the average ms per call over `reps` calls. */
 int qpalm_b200_bench_dsyrk(c_int n, c_int k, c_int reps, double *ms_out);
 int qpalm_b200_bench_potrf(c_int n, c_int reps, double *ms_out);
+/* one rank-k dataflow sweep (updown_flow.cu) on an n x n factor, k <= 64: average ms per sweep */
+int qpalm_b200_bench_updown(c_int n, c_int k, c_int reps, double *ms_out);
 /* FP64 tensor-pipe (DMMA) issue-rate peak in TFLOP/s: register-resident mma.sync chains, no memory traffic. */
 int qpalm_b200_bench_dmma_peak(double *tflops_out);
 /* dense matrix-vector kernels at the solver's shapes (At is n x m): ms per A*x (column dots) and per A'*y (row sums) */

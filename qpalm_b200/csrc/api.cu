@@ -383,8 +383,10 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 // factor: a static model, so the choice never depends on timing; sparse factor: the measured time of the last sweep
 // against the last refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
-  if (k <= 0 || k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
+  if (k <= 0) return false;
   if (e->sh_world > 1) return false;   // row-sharded: the entering rows live on different ranks; refactorise (allreduced H)
+  const bool flow = !e->sp && e->updown_flow_ok && e->npad >= 256;   // one-launch dataflow sweep, <= 64 ranks each (updown_flow.cu)
+  if (!flow && k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->updown_force) return true;
   if (e->sp) {   // sparse factor: k sweeps of <= 8 ranks along etree paths; measured cost of the last one vs the last refactorisation
     const double t_sweep = e->last_updown_ms > 0 ? e->last_updown_ms : 0.0;   // unknown yet: try it once
@@ -395,8 +397,14 @@ static bool prefer_updown(const Engine *e, int k) {
   // cost a fraction of a millisecond: follow the reference's own choice (rank update) so that tiny ill-conditioned
   // problems (tests/src/test_dua_inf_qp.c) round alike.
   if (e->npad <= 128) return true;
-  const double t_ud = (e->npad / 32.0) * (0.060 + 0.008 * k);                                   // ms, B200 (measured 83 us per 32-column panel step at n = 8000)
   const double t_rf = (e->npad / 128.0) * 0.12 + ((double)e->n * e->n * e->n / 3.0) / 25e9;      // ms: panel chain + DMMA flops
+  if (flow) {
+    // the sweep is a chain of npad/32 panel steps whose length does not depend on the rank (<= 64 columns per sweep),
+    // plus the refresh of the inverted diagonal blocks
+    const double t_ud = ((k + 63) / 64) * (e->npad / 32.0) * e->updown_panel_ms + 0.08;
+    return t_ud < t_rf;
+  }
+  const double t_ud = (e->npad / 32.0) * (0.060 + 0.008 * k);                                   // ms, B200 (measured 83 us per 32-column panel step at n = 8000)
   return t_ud < t_rf;
 }
 
@@ -420,6 +428,7 @@ static void update_sigma(QPALMWorkspace *work, Pending &pend) {
     work->solver->reset_newton = TRUE;
   } else {   // ldlupdate_sigma_changed (solver_interface.c:443-503)
     sigma_changed_update(e, (int)work->nb_sigma_changed);
+    e->n_sigma_update++; e->sigma_update_rank_sum += work->nb_sigma_changed;
     pend.kind = 2;
   }
 }
@@ -451,6 +460,7 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
     cudaStreamSynchronize(e->stream);
   }
   Pending pend{0};
+  static const bool trace = getenv("QPALM_B200_TRACE") != nullptr;
   const bool prox0 = st->proximal != 0;
   (void)prox0;
   if (st->enable_dual_termination) {   // qpalm.c:459-472
@@ -583,6 +593,8 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
       else if (na) {
         if (ne + nl > 0) { if (prefer_updown(e, ne + nl)) do_updown = true; else need_refactor = true; }
       } else factor_q = true;
+      if (trace) fprintf(stderr, "[qpalm_b200 trace] iter %ld out %ld active %d enter %d leave %d -> %s\n", (long)iter, (long)iter_out, na, ne, nl,
+                         do_updown ? "rank update" : (need_refactor ? (from_scratch ? "refactor (scratch)" : "refactor (incremental H)") : (factor_q ? "factor Q" : "reuse factor")));
       if (do_updown) {
         step_compact_lists(e);   // commits active <- candidate and lists enter / leave
         int hinfo = 0;
@@ -745,5 +757,6 @@ extern "C" int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *
   out->sparse_factor_nnz = e->sp ? sparse_chol_info(e->sp)->nnzL : 0;
   out->sparse_supernodes = e->sp ? sparse_chol_info(e->sp)->nsuper : 0;
   out->sparse_levels = e->sp ? sparse_chol_info(e->sp)->nlevels : 0;
+  out->sigma_update_calls = e->n_sigma_update; out->sigma_update_rank_sum = e->sigma_update_rank_sum;
   return 0;
 }

@@ -42,6 +42,12 @@ void chol_solve_release(cudaStream_t s);
 int chol_updown(cudaStream_t s, int npad, double *L, int ld, double *W, int ldw, int k, int sign,
                 double *coef, int *info_dev);
 
+// One-launch dataflow sweep (updown_flow.cu): L <- chol(L L' + W S W'), S = diag(+1 x kpos, -1 x (k - kpos)), k <= 64 per call;
+// W (npad x k, ldw) is only read.  Returns 0 when it ran, 1 when the cooperative kernel is not available (use chol_updown).
+int chol_updown_flow(cudaStream_t s, int npad, double *L, int ld, const double *W, int ldw, int k, int kpos, int *info_dev);
+int chol_updown_flow_max_rank();
+void chol_updown_flow_release(cudaStream_t s);
+
 // L(lower) <- H(lower) + diag_add * I on the leading n x n block; pad block <- identity.
 int copy_lower_add_diag(cudaStream_t s, int n, int npad, const double *H, double *L, int ld, double diag_add);
 

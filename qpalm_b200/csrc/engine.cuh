@@ -98,11 +98,13 @@ struct Engine {
   int *info_dev = nullptr;
   // statistics (QPALMB200Stats)
   long long launches0 = 0;
-  long long n_inner = 0, n_outer = 0, n_refactor = 0, refactor_active_sum = 0, n_updown = 0, updown_rank_sum = 0, n_spmv = 0;
+  long long n_inner = 0, n_outer = 0, n_refactor = 0, refactor_active_sum = 0, n_updown = 0, updown_rank_sum = 0, n_spmv = 0, n_sigma_update = 0, sigma_update_rank_sum = 0;
   double alg_bytes = 0, dense_flops = 0, ms_factor = 0, ms_updown = 0, ms_total = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
   // tunables
   int updown_max_rank = 8;           // one sweep of the rank-k kernel
+  bool updown_flow_ok = true;        // cleared when the cooperative dataflow sweep cannot launch on this device
+  double updown_panel_ms = 0.0115;   // static cost-model constant: one 32-column panel step of the dataflow sweep (B200)
   int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
   double last_updown_ms = -1.0;      // CUDA-event time of the most recent update/downdate call (sparse cost model)
   double last_refactor_ms = -1.0;    // CUDA-event time of the most recent refactorisation (cost model input)

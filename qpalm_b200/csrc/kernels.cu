@@ -459,13 +459,15 @@ __global__ void k_gather_csr(int npad, const int *__restrict__ p, const int *__r
     for (int k = p[row] + threadIdx.x; k < p[row + 1]; k += blockDim.x) col[ci[k]] = x[k] * s;
   }
 }
-static int gather_rows(Engine *e, const int *list, const double *scale, bool scale_by_row, int cnt, int kpad) {
+static int gather_rows(Engine *e, const int *list, const double *scale, bool scale_by_row, int cnt, int kpad, int col0 = 0) {
+  if (kpad <= 0) return 0;
+  double *W = e->W + (size_t)e->ld * col0;
   if (e->A_dense) {
     dim3 grid(cdiv(e->npad, 256), kpad);
-    QB_LAUNCH(k_gather_dense, grid, 256, 0, e->stream, e->n, e->npad, e->At, list, scale, scale_by_row ? 1 : 0, cnt, e->W, e->ld, e->m_lo, e->m_loc);
+    QB_LAUNCH(k_gather_dense, grid, 256, 0, e->stream, e->n, e->npad, e->At, list, scale, scale_by_row ? 1 : 0, cnt, W, e->ld, e->m_lo, e->m_loc);
   } else {
     QB_LAUNCH(k_gather_csr, kpad, 256, 0, e->stream, e->npad, e->A_csr.p, e->A_csr.i, e->A_csr.x, list, scale,
-              scale_by_row ? 1 : 0, cnt, e->W, e->ld);
+              scale_by_row ? 1 : 0, cnt, W, e->ld);
   }
   return 0;
 }
@@ -581,9 +583,49 @@ int step_newton_refactor(Engine *e, bool with_constraints, bool from_scratch, do
   return 0;
 }
 
+// the one-launch dataflow sweep (updown_flow.cu) serves factors of at least two 128-column blocks; below that the
+// per-panel kernels of dense.cu cost a handful of launches
+static bool use_updown_flow(const Engine *e) {
+  static const int min_npad = [] { const char *s = getenv("QPALM_B200_UPDOWN_FLOW_MIN"); return s ? atoi(s) : 256; }();
+  return !e->sp && e->npad >= min_npad && e->updown_flow_ok;
+}
+
+// L <- chol(L L' + sum_enter w w' - sum_leave w w'): entering and leaving rows share sweeps of <= 64 columns
+// (weight pattern S = diag(+1.., -1..), see updown_flow.cu)
+static int updown_flow_lists(Engine *e, const int *pos, const double *pos_scale, bool pos_by_row, int npos,
+                             const int *neg, const double *neg_scale, bool neg_by_row, int nneg) {
+  const int KMAX = chol_updown_flow_max_rank();
+  int ip = 0, in = 0;
+  while (ip < npos || in < nneg) {
+    const int kp = (npos - ip < KMAX) ? npos - ip : KMAX;
+    const int kn = (nneg - in < KMAX - kp) ? nneg - in : KMAX - kp;
+    if (int r = gather_rows(e, pos + ip, pos_by_row ? pos_scale : pos_scale + ip, pos_by_row, kp, kp, 0)) return r;
+    if (int r = gather_rows(e, neg + in, neg_by_row ? neg_scale : neg_scale + in, neg_by_row, kn, kn, kp)) return r;
+    const int rc = chol_updown_flow(e->stream, e->npad, e->L, e->ld, e->W, e->ld, kp + kn, kp, e->info_dev);
+    // 1: cooperative launch unavailable -- it fails on the first chunk or never, so nothing has been applied and the caller
+    // can fall back to the per-panel kernels; < 0: CUDA error
+    if (rc) return (rc == 1 && ip == 0 && in == 0) ? 1 : (rc < 0 ? rc : -999);
+    e->n_updown++; e->updown_rank_sum += kp + kn;
+    e->dense_flops += 2.0 * (kp + kn) * (double)e->n * e->n;
+    e->alg_bytes += 2.0 * 8.0 * (double)e->n * (e->n + 1) / 2;
+    ip += kp; in += kn;
+  }
+  return 0;
+}
+
 // ldlupdate_entering_constraints / ldldowndate_leaving_constraints (solver_interface.c:407-441)
 int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
+  if (use_updown_flow(e)) {
+    const int rc = updown_flow_lists(e, e->enter, e->sqrt_sigma, true, nb_enter, e->leave, e->sqrt_sigma, true, nb_leave);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r;
+      QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
+      return 0;
+    }
+    e->updown_flow_ok = false;   // no cooperative launch on this device / partition: per-panel kernels from now on
+  }
   for (int pass = 0; pass < 2; pass++) {
     const int *list = pass == 0 ? e->enter : e->leave;
     const int cnt = pass == 0 ? nb_enter : nb_leave;
@@ -611,6 +653,16 @@ int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
 // ldlupdate_sigma_changed (solver_interface.c:443-503): rank-k update with sqrt(sigma_new - sigma_old) * a_j
 int sigma_changed_update(Engine *e, int nb_changed) {
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
+  if (use_updown_flow(e)) {
+    const int rc = updown_flow_lists(e, e->changed, e->w_pos, false, nb_changed, nullptr, nullptr, false, 0);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r;
+      QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream));
+      return 0;
+    }
+    e->updown_flow_ok = false;
+  }
   for (int off = 0; off < nb_changed; off += 8) {
     const int k = nb_changed - off < 8 ? nb_changed - off : 8;
     if (e->sp) {
@@ -1610,7 +1662,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   const size_t LL = e->sp ? 1 : (size_t)e->ld * e->npad;
   size_t free_b = 0, total_b = 0;
   QB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  e->wcols = e->sp ? 16 : round_up(m < 16 ? 16 : (m > 2048 ? 2048 : m), 16);
+  e->wcols = e->sp ? 16 : round_up(m < 64 ? 64 : (m > 2048 ? 2048 : m), 16);   // >= one 64-column update sweep
   if (e->sp) {
     rc |= dv(&e->spL, sparse_chol_factor_doubles(e->sp));
     if (need_LQ) rc |= dv(&e->spLQ, sparse_chol_factor_doubles(e->sp));
@@ -1645,6 +1697,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   e->launches0 = g_kernel_launches;
   if (const char *s = getenv("QPALM_B200_UPDOWN_MAX_RANK")) e->updown_max_rank = atoi(s);
   if (const char *s = getenv("QPALM_B200_UPDOWN_FORCE")) e->updown_force = atoi(s);
+  if (const char *s = getenv("QPALM_B200_UPDOWN_PANEL_MS")) e->updown_panel_ms = atof(s);
   QB_CUDA_TRY(cudaDeviceSynchronize());
   lap("factor storage + scratch");
   *out = e;
@@ -1670,7 +1723,7 @@ void engine_destroy(Engine *e) {
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs0) cudaEventDestroy(e->evs0);
   if (e->evs1) cudaEventDestroy(e->evs1);
-  if (e->stream) { chol_solve_release(e->stream); cudaStreamDestroy(e->stream); }
+  if (e->stream) { chol_solve_release(e->stream); chol_updown_flow_release(e->stream); cudaStreamDestroy(e->stream); }
   delete e;
 }
 

@@ -220,7 +220,19 @@ extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *
   QB_CUDA_TRY(cudaMemcpy(e->L, Lp.data(), sizeof(double) * Lp.size(), cudaMemcpyHostToDevice));
   QB_CUDA_TRY(cudaMemset(e->info_dev, 0, sizeof(int)));
   rc = 0;
-  for (int off = 0; off < k && !rc; off += 8) {
+  static const int flow_min = [] { const char *s = getenv("QPALM_B200_UPDOWN_FLOW_MIN"); return s ? atoi(s) : 256; }();
+  bool flow = npad >= flow_min;   // same dispatch as step_newton_updown: one dataflow launch per <= 64 columns
+  const int chunk = flow ? chol_updown_flow_max_rank() : 8;
+  for (int off = 0; off < k && !rc && flow; off += chunk) {
+    const int kk = k - off < chunk ? k - off : chunk;
+    std::vector<double> Wp((size_t)ld * kk, 0.0);
+    for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
+    QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    QB_CUDA_TRY(cudaMemcpy(e->W, Wp.data(), sizeof(double) * Wp.size(), cudaMemcpyHostToDevice));
+    rc = chol_updown_flow(e->stream, npad, e->L, ld, e->W, ld, kk, update ? kk : 0, e->info_dev);
+    if (rc == 1 && off == 0) { flow = false; rc = 0; }   // no cooperative launch here: per-panel kernels below
+  }
+  for (int off = 0; off < k && !rc && !flow; off += 8) {
     const int kk = k - off < 8 ? k - off : 8;
     std::vector<double> Wp((size_t)ld * 8, 0.0);
     for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
@@ -399,6 +411,41 @@ extern "C" int qpalm_b200_bench_potrf(c_int n_, c_int reps, double *ms_out) {
   *ms_out = total / (reps > 0 ? reps : 1);
   int hinfo = 0; cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
   cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(A); cudaFree(L); cudaFree(X); cudaFree(info);
+  return rc ? rc : hinfo;
+}
+
+// one rank-k sweep (update, then the matching downdate so the factor stays bounded) on a factored random SPD matrix:
+// ms per sweep, averaged over 2 * reps sweeps
+extern "C" int qpalm_b200_bench_updown(c_int n_, c_int k_, c_int reps, double *ms_out) {
+  const int n = round_up((int)n_, 128), k = (int)k_;
+  if (k < 1 || k > chol_updown_flow_max_rank()) return 1;
+  double *L = nullptr, *X = nullptr, *W = nullptr; int *info = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&L, sizeof(double) * (size_t)n * n));
+  QB_CUDA_TRY(cudaMalloc(&X, sizeof(double) * (size_t)n * 128));
+  QB_CUDA_TRY(cudaMalloc(&W, sizeof(double) * (size_t)n * k));
+  QB_CUDA_TRY(cudaMalloc(&info, sizeof(int)));
+  QB_CUDA_TRY(cudaMemset(info, 0, sizeof(int)));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  QB_LAUNCH(k_fill_rand, 1024, 256, 0, s, L, (size_t)n * n, 99ull);
+  QB_LAUNCH(k_fill_rand, 256, 256, 0, s, W, (size_t)n * k, 7ull);
+  dim3 g(cdiv(n, 256), n);
+  QB_LAUNCH(k_make_spd, g, 256, 0, s, n, L);
+  int rc = potrf_lower(s, n, L, n, X, info);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float total = 0;
+  for (int r = 0; r < reps + 1 && !rc; r++) {
+    cudaEventRecord(a, s);
+    rc = chol_updown_flow(s, n, L, n, W, n, k, k, info);
+    if (!rc) rc = chol_updown_flow(s, n, L, n, W, n, k, 0, info);
+    cudaEventRecord(b, s);
+    QB_CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    if (r > 0) total += ms;
+  }
+  *ms_out = total / (2.0 * (reps > 0 ? reps : 1));
+  int hinfo = 0; cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+  chol_updown_flow_release(s);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(L); cudaFree(X); cudaFree(W); cudaFree(info);
   return rc ? rc : hinfo;
 }
 

@@ -201,6 +201,16 @@ class Qpalm:
     def info(self) -> QPALMInfo:
         return self._work.contents.info.contents
 
+    def stats(self) -> abi.QPALMB200Stats:
+        """Counters of the CUDA engine (qpalm_b200_get_stats, an additive entry point: "b200" only)."""
+        f = self.lib.qpalm_b200_get_stats
+        f.argtypes = [C.POINTER(QPALMWorkspace), C.POINTER(abi.QPALMB200Stats)]
+        f.restype = C.c_int
+        st = abi.QPALMB200Stats()
+        if f(self._work, C.byref(st)) != 0:
+            raise RuntimeError("qpalm_b200_get_stats failed")
+        return st
+
     def vec(self, name: str, length: int) -> np.ndarray:
         p = getattr(self._work.contents, name)
         return np.ctypeslib.as_array(p, shape=(length,)).copy() if length else np.zeros(0)

@@ -18,6 +18,13 @@ elif what == "syrk":
     lib.qpalm_b200_bench_dsyrk.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double)]
     rc = lib.qpalm_b200_bench_dsyrk(n, k, 2, C.byref(ms))
     print("syrk", n, k, "ms", ms.value, "TFLOP/s", n * n * k / ms.value / 1e9)
+elif what == "updown":
+    lib.qpalm_b200_bench_updown.argtypes = [abi.c_int, abi.c_int, abi.c_int, C.POINTER(C.c_double)]
+    for k in ([int(sys.argv[3])] if len(sys.argv) > 3 else [1, 8, 32, 33, 64]):
+        rc = lib.qpalm_b200_bench_updown(n, k, 3, C.byref(ms))
+        npad = (n + 127) // 128 * 128
+        print("updown sweep n", n, "k", k, "rc", rc, "ms", round(ms.value, 4), "us per 32-column panel", round(1e3 * ms.value / (npad / 32), 3),
+              "GB/s (2 B_L)", round(2 * 8 * npad * (npad + 1) / 2 / ms.value / 1e6, 1))
 elif what == "potrf_prof":
     # per-kernel CUDA-event breakdown of one blocked Cholesky
     lib.qpalm_b200_bench_potrf.argtypes = [abi.c_int, abi.c_int, C.POINTER(C.c_double)]
