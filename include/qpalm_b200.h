@@ -293,6 +293,7 @@ int qpalm_b200_bench_dsyrk(c_int n, c_int k, c_int reps, double *ms_out);
 int qpalm_b200_bench_potrf(c_int n, c_int reps, double *ms_out);
 /* one rank-k dataflow sweep (updown_flow.cu) on an n x n factor, k <= 64: average ms per sweep */
 int qpalm_b200_bench_updown(c_int n, c_int k, c_int reps, double *ms_out);
+int qpalm_b200_bench_updown_clocks(c_int n, c_int k, long long *out32);
 /* FP64 tensor-pipe (DMMA) issue-rate peak in TFLOP/s: register-resident mma.sync chains, no memory traffic. */
 int qpalm_b200_bench_dmma_peak(double *tflops_out);
 /* dense matrix-vector kernels at the solver's shapes (At is n x m): ms per A*x (column dots) and per A'*y (row sums) */

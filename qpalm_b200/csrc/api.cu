@@ -401,7 +401,10 @@ static bool prefer_updown(const Engine *e, int k) {
   if (flow) {
     // the sweep is a chain of npad/32 panel steps whose length does not depend on the rank (<= 64 columns per sweep),
     // plus the refresh of the inverted diagonal blocks
-    const double t_ud = ((k + 63) / 64) * (e->npad / 32.0) * e->updown_panel_ms + 0.08;
+    // (measured on B200: 13.5 us per panel in the 32-column shape, 17.9 us in the 64-column shape)
+    const int full = k / 64, rem = k % 64;
+    const double per_panel = full * e->updown_panel_ms64 + (rem > 32 ? e->updown_panel_ms64 : (rem > 0 ? e->updown_panel_ms : 0.0));
+    const double t_ud = (e->npad / 32.0) * per_panel + 0.08;
     return t_ud < t_rf;
   }
   const double t_ud = (e->npad / 32.0) * (0.060 + 0.008 * k);                                   // ms, B200 (measured 83 us per 32-column panel step at n = 8000)

@@ -44,7 +44,8 @@ int chol_updown(cudaStream_t s, int npad, double *L, int ld, double *W, int ldw,
 
 // One-launch dataflow sweep (updown_flow.cu): L <- chol(L L' + W S W'), S = diag(+1 x kpos, -1 x (k - kpos)), k <= 64 per call;
 // W (npad x k, ldw) is only read.  Returns 0 when it ran, 1 when the cooperative kernel is not available (use chol_updown).
-int chol_updown_flow(cudaStream_t s, int npad, double *L, int ld, const double *W, int ldw, int k, int kpos, int *info_dev);
+int chol_updown_flow(cudaStream_t s, int npad, double *L, int ld, const double *W, int ldw, int k, int kpos, int *info_dev,
+                     long long *clk_dev = nullptr /* instrumented runs: 32 clock64 stamps of the chain CTA */);
 int chol_updown_flow_max_rank();
 void chol_updown_flow_release(cudaStream_t s);
 

@@ -104,7 +104,7 @@ struct Engine {
   // tunables
   int updown_max_rank = 8;           // one sweep of the rank-k kernel
   bool updown_flow_ok = true;        // cleared when the cooperative dataflow sweep cannot launch on this device
-  double updown_panel_ms = 0.0115;   // static cost-model constant: one 32-column panel step of the dataflow sweep (B200)
+  double updown_panel_ms = 0.0135, updown_panel_ms64 = 0.0179;   // static cost model: one panel step of the dataflow sweep, <= 32 / <= 64 ranks (B200)
   int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
   double last_updown_ms = -1.0;      // CUDA-event time of the most recent update/downdate call (sparse cost model)
   double last_refactor_ms = -1.0;    // CUDA-event time of the most recent refactorisation (cost model input)

@@ -449,6 +449,32 @@ extern "C" int qpalm_b200_bench_updown(c_int n_, c_int k_, c_int reps, double *m
   return rc ? rc : hinfo;
 }
 
+// stage clocks of the chain CTA of one sweep (panels 100 and 101): out32 receives up to 32 clock64 stamps
+extern "C" int qpalm_b200_bench_updown_clocks(c_int n_, c_int k_, long long *out32) {
+  const int n = round_up((int)n_, 128), k = (int)k_;
+  double *L = nullptr, *X = nullptr, *W = nullptr; int *info = nullptr; long long *clk = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&L, sizeof(double) * (size_t)n * n));
+  QB_CUDA_TRY(cudaMalloc(&X, sizeof(double) * (size_t)n * 128));
+  QB_CUDA_TRY(cudaMalloc(&W, sizeof(double) * (size_t)n * k));
+  QB_CUDA_TRY(cudaMalloc(&info, sizeof(int)));
+  QB_CUDA_TRY(cudaMalloc(&clk, sizeof(long long) * 32));
+  QB_CUDA_TRY(cudaMemset(info, 0, sizeof(int)));
+  QB_CUDA_TRY(cudaMemset(clk, 0, sizeof(long long) * 32));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  QB_LAUNCH(k_fill_rand, 1024, 256, 0, s, L, (size_t)n * n, 99ull);
+  QB_LAUNCH(k_fill_rand, 256, 256, 0, s, W, (size_t)n * k, 7ull);
+  dim3 g(cdiv(n, 256), n);
+  QB_LAUNCH(k_make_spd, g, 256, 0, s, n, L);
+  int rc = potrf_lower(s, n, L, n, X, info);
+  if (!rc) rc = chol_updown_flow(s, n, L, n, W, n, k, k, info);          // warm
+  if (!rc) rc = chol_updown_flow(s, n, L, n, W, n, k, 0, info, clk);
+  QB_CUDA_TRY(cudaStreamSynchronize(s));
+  QB_CUDA_TRY(cudaMemcpy(out32, clk, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
+  chol_updown_flow_release(s);
+  cudaStreamDestroy(s); cudaFree(L); cudaFree(X); cudaFree(W); cudaFree(info); cudaFree(clk);
+  return rc;
+}
+
 // ---- batch API: implemented in batch.cu ---------------------------------------------------------------
 
 // FP64 tensor-pipe issue-rate peak: register-resident mma.sync m8n8k4 chains, no memory traffic.
