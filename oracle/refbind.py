@@ -27,6 +27,9 @@ REF_QPS_LIB = os.path.join(HERE, "_ref", "libqpalm_qps_ref.so")
 ORACLE_LIB = os.path.join(HERE, "liboracle.so")
 
 
+_BLAS = []
+
+
 def preload_blas():
     """The compiled reference links the OpenBLAS bundled in the opencv wheel (oracle/Makefile); that library needs its
     sibling libgfortran/libquadmath, which are not on the loader path."""
@@ -34,9 +37,21 @@ def preload_blas():
     for pat in ("libquadmath*", "libgfortran*", "libopenblasp*"):
         for f in sorted(glob.glob(os.path.join(d, pat))):
             try:
-                C.CDLL(f, mode=os.RTLD_GLOBAL | os.RTLD_NOW)
+                h = C.CDLL(f, mode=os.RTLD_GLOBAL | os.RTLD_NOW)
+                if "openblas" in os.path.basename(f):
+                    _BLAS.append(h)
             except OSError:
                 pass
+
+
+def set_blas_threads(n: int) -> None:
+    """Thread count of the OpenBLAS the compiled reference uses (its supernodal Cholesky calls BLAS-3); QPALM itself is
+    single-threaded.  bench.py: 1 per worker process for the batch sample, all host cores for the dense sample."""
+    for h in _BLAS:
+        try:
+            h.openblas_set_num_threads(int(n))
+        except AttributeError:
+            pass
 
 
 def have_reference() -> bool:

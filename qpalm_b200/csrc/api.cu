@@ -384,8 +384,8 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 // against the last refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0) return false;
-  if (e->sh_world > 1) return false;   // row-sharded: the entering rows live on different ranks; refactorise (allreduced H)
   const bool flow = !e->sp && e->updown_flow_ok && e->npad >= 256;   // one-launch dataflow sweep, <= 64 ranks each (updown_flow.cu)
+  if (e->sh_world > 1 && !flow) return false;   // row-sharded: only the dataflow path allreduces the gathered rows
   if (!flow && k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->updown_force) return true;
   if (e->sp) {   // sparse factor: k sweeps of <= 8 ranks along etree paths; measured cost of the last one vs the last refactorisation

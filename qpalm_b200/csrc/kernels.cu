@@ -601,6 +601,9 @@ static int updown_flow_lists(Engine *e, const int *pos, const double *pos_scale,
     const int kn = (nneg - in < KMAX - kp) ? nneg - in : KMAX - kp;
     if (int r = gather_rows(e, pos + ip, pos_by_row ? pos_scale : pos_scale + ip, pos_by_row, kp, kp, 0)) return r;
     if (int r = gather_rows(e, neg + in, neg_by_row ? neg_scale : neg_scale + in, neg_by_row, kn, kn, kp)) return r;
+    // row-sharded problem: every rank gathered the rows it owns (zero columns for the others); the sum over ranks is the full
+    // n x k block, and every rank then runs the same sweep on its replica of L
+    if (e->sh_world > 1) { if (int r = shard_allreduce(e->W, e->W, (size_t)e->ld * (kp + kn), false, e->stream)) return r; }
     const int rc = chol_updown_flow(e->stream, e->npad, e->L, e->ld, e->W, e->ld, kp + kn, kp, e->info_dev);
     // 1: cooperative launch unavailable -- it fails on the first chunk or never, so nothing has been applied and the caller
     // can fall back to the per-panel kernels; < 0: CUDA error
