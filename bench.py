@@ -344,14 +344,48 @@ def tensor_roofline(lib, n, k_avg, dense):
             "syrk_alone_tflops": syrk_tf, "potrf_alone_tflops": potrf_tf}
 
 
+def sparse_spmv_roofline(lib, hbm):
+    """Q x, A x, A' y over CSR / CSC (k_csr_spmv: a warp per row / column, 128-bit value + 64-bit index loads) at the C1 and
+    C2 shapes of BASELINE.json.  bytes = 12 nnz + 4 (rows + 1) + 8 (rows + cols) per product (SURVEY 8(d) storage model)."""
+    lib.qpalm_b200_bench_spmv.argtypes = [C.POINTER(abi.SolverSparse), C.POINTER(abi.SolverSparse), abi.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(abi.c_int)]
+    out = {}
+    shapes = {"C1 random sparse n=1000 m=2000 density 0.05": lambda: problems.random_qp(1000, 2000, 0.05, 0.007, seed=1),
+              "C2 stand-in (SYNTHETIC grid QP, CONT-300 class) n=90000 m=359102": lambda: problems.grid_qp(300, seed=0)}
+    for name, make in shapes.items():
+        p = make()
+        ms, nnz = (C.c_double * 3)(), (abi.c_int * 3)()
+        rc = lib.qpalm_b200_bench_spmv(p.A.ptr(), p.Q.ptr(), 50, ms, nnz)
+        if rc:
+            out[name] = {"unavailable": f"qpalm_b200_bench_spmv rc {rc}"}
+            continue
+        n, m = p.n, p.m
+        dims = {"A_times_x": (m, n), "At_times_y": (n, m), "Q_times_x": (n, n)}
+        blk = {}
+        for k, key in enumerate(dims):
+            rows, cols = dims[key]
+            by = 12.0 * nnz[k] + 4.0 * (rows + 1) + 8.0 * (rows + cols)
+            gbs = by / (ms[k] * 1e-3) / 1e9
+            blk[key] = {"achieved": gbs, "frac": gbs / hbm, "us": 1e3 * ms[k], "nnz": int(nnz[k]), "bytes": by}
+        blk["note"] = ("working set %.1f MB: L2-resident after the first touch (126 MB L2), so this is launch latency + L2 bandwidth, not HBM"
+                       % ((12.0 * (nnz[0] + nnz[2])) / 1e6)) if 12.0 * (nnz[0] + nnz[2]) < 100e6 else "working set exceeds L2"
+        out[name] = blk
+    return out
+
+
 def hbm_roofline(lib, n, m):
     hbm, src = measured_peaks()
     a, b = C.c_double(0), C.c_double(0)
     lib.qpalm_b200_bench_gemv(n, m, 20, C.byref(a), C.byref(b))
     bytes_ = 8.0 * n * m
-    return {"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": src,
-            "A_times_x": {"achieved": bytes_ / (a.value * 1e-3) / 1e9, "frac": bytes_ / (a.value * 1e-3) / 1e9 / hbm},
-            "At_times_y": {"achieved": bytes_ / (b.value * 1e-3) / 1e9, "frac": bytes_ / (b.value * 1e-3) / 1e9 / hbm}}
+    out = {"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": src,
+           "A_times_x": {"achieved": bytes_ / (a.value * 1e-3) / 1e9, "frac": bytes_ / (a.value * 1e-3) / 1e9 / hbm},
+           "At_times_y": {"achieved": bytes_ / (b.value * 1e-3) / 1e9, "frac": bytes_ / (b.value * 1e-3) / 1e9 / hbm}}
+    try:
+        out["sparse"] = sparse_spmv_roofline(lib, hbm)
+    except Exception as ex:      # never lose the bench line over a side measurement
+        out["sparse"] = {"unavailable": repr(ex)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -360,10 +394,17 @@ def hbm_roofline(lib, n, m):
 # dominant kernel per batch engine (share of the step from the ncu launch lists under profiles/): the persistent engine IS
 # one kernel; in the lock-step engine the single-CTA diagonal-block factorisation leads (39 %)
 DOMINANT_KERNEL = {"persistent": "kbp_solve", "lockstep": "k_diag_block"}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the `ncu --set full` capture of this command at the default
-# --batch 512 (profiles/r01e_ncu_full_kbp_solve.txt, the 4-CTA/SM shape the dispatcher picks for 512: 56.02 GB read + 58.58 GB written;
-# the 3-CTA/SM shape moved 34.66 + 38.37 GB, profiles/r01d_ncu_full_kbp_solve.txt)
-NCU_TRAFFIC_BYTES = {("kbp_solve", 512): 56.016316e9 + 58.581683e9}
+def ncu_traffic(kernel, nb):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, read from profiles/ncu_traffic.json --
+    written by tools/ncu_full_summary.py from the `ncu --set full` capture of this command, together with the capture's file
+    name and the batch size it was taken at.  null when no capture matches the batch size being benchmarked."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    for ent in json.load(open(path)).get(kernel, []):
+        if int(ent.get("batch", -1)) == int(nb):
+            return float(ent["dram_bytes"]), ent.get("source")
+    return None, None
 
 
 def batch_algorithmic_bytes(n, m, stats):
@@ -391,8 +432,9 @@ def batch_roofline(n, m, nb, r, steps):
         bytes_per_launch = nb * 3 * 8.0 * 128 * 129 / 2
         note = "per launch: every instance's 128 x 128 diagonal block read + written, inverse written (upper bound: masked instances skip)"
     ach = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(r["dominant"], nb)
     return {"bound": "hbm", "kernel": r["dominant"], "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": NCU_TRAFFIC_BYTES.get((r["dominant"], nb)), "traffic_source": "profiles/r01e_ncu_full_kbp_solve.txt",
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": src, "launches_timed": launches, "ms_per_launch": per_launch_ms, "share_of_step": ms / max(r["dev_ms"], 1e-9),
             "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
 

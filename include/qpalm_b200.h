@@ -296,8 +296,12 @@ int qpalm_b200_bench_updown(c_int n, c_int k, c_int reps, double *ms_out);
 int qpalm_b200_bench_updown_clocks(c_int n, c_int k, long long *out32);
 /* FP64 tensor-pipe (DMMA) issue-rate peak in TFLOP/s: register-resident mma.sync chains, no memory traffic. */
 int qpalm_b200_bench_dmma_peak(double *tflops_out);
+/* scalar FP64 FMA (DFMA) issue-rate peak in TFLOP/s, same method: the bound of the kernels that use plain fma() */
+int qpalm_b200_bench_dfma_peak(double *tflops_out);
 /* dense matrix-vector kernels at the solver's shapes (At is n x m): ms per A*x (column dots) and per A'*y (row sums) */
 int qpalm_b200_bench_gemv(c_int n, c_int m, c_int reps, double *ms_cols_out, double *ms_rows_out);
+/* sparse products through the solver's CSR / CSC kernels: out3 = ms per A x, A' y, Q x; nnz3 = stored entries each one streams */
+int qpalm_b200_bench_spmv(const solver_sparse *A, const solver_sparse *Q, c_int reps, double *out3, c_int *nnz3);
 
 /* ------------------------------------------------------------------------------------------------
  * Part 2b -- row-sharding of one large dense QP over the GPUs of a box (additive; SURVEY.md 8(e), BASELINE config 3).
@@ -340,9 +344,10 @@ int  qpalm_b200_batch_solve(QPALMB200Batch *batch, c_int nb, const c_float *q, c
 int  qpalm_b200_batch_upload(QPALMB200Batch *batch, c_int nb, const c_float *q, const c_float *bmin, const c_float *bmax);
 int  qpalm_b200_batch_solve_resident(QPALMB200Batch *batch, c_int nb, double *device_ms);
 int  qpalm_b200_batch_download(QPALMB200Batch *batch, c_int nb, c_float *x, c_float *y, QPALMInfo *info);
-/* totals of the last solve over instances 0..nb-1: out5 = {inner iterations, outer iterations, refactorisations,
- * sum of |J| over the refactorisations, engine (1 lock-step, 2 persistent)} -- inputs of the SURVEY 8(d) byte model */
-int  qpalm_b200_batch_stats(QPALMB200Batch *batch, c_int nb, double *out5);
+/* totals of the last solve over instances 0..nb-1: out8 = {inner iterations, outer iterations, refactorisations,
+ * sum of |J| over the refactorisations, engine (1 lock-step, 2 persistent), rank-k update sweeps, sum of their ranks,
+ * downdates that lost definiteness (followed by a refactorisation)} -- inputs of the SURVEY 8(d) byte model */
+int  qpalm_b200_batch_stats(QPALMB200Batch *batch, c_int nb, double *out8);
 /* persistent engine, QPALM_B200_BATCH_PROF=1 at setup: per-instance SM-clock totals of 16 phases of the last solve */
 int  qpalm_b200_batch_phase_profile(QPALMB200Batch *batch, c_int nb, long long *out);
 long long qpalm_b200_batch_last_launches(const QPALMB200Batch *batch);   /* kernels launched by the last solve */

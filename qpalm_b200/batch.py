@@ -91,11 +91,12 @@ class Batch:
         return x, y, _infos(info, nb)
 
     def stats(self, nb):
-        out = np.zeros(5)
+        out = np.zeros(8)
         if self.lib.qpalm_b200_batch_stats(self.h, nb, fptr(out)):
             raise RuntimeError("batch_stats failed")
         return dict(inner=out[0], outer=out[1], refactorizations=out[2], refactor_J_sum=out[3],
-                    engine={1: "lockstep", 2: "persistent"}.get(int(out[4]), "?"))
+                    engine={1: "lockstep", 2: "persistent"}.get(int(out[4]), "?"),
+                    updown_sweeps=out[5], updown_rank_sum=out[6], updown_failed=out[7])
 
     def last_launches(self):
         return int(self.lib.qpalm_b200_batch_last_launches(self.h))

@@ -139,8 +139,9 @@ extern "C" QPALMWorkspace *qpalm_setup(const QPALMData *data, const QPALMSetting
   work->data->bmin = vcopy(data->bmin, m); work->data->bmax = vcopy(data->bmax, m); work->data->q = vcopy(data->q, n);
   // Host copies of the matrices are kept only for modest sizes (they are never read by the solver; the
   // device holds the scaled working copies).  The reference keeps scaled CHOLMOD copies here.
-  const c_int *Ap = (const c_int *)data->A->p, *Qp = (const c_int *)data->Q->p;
-  if ((size_t)Ap[n] + (size_t)Qp[n] <= (size_t)1 << 24) {
+  // (work->data->A / Q stay NULL above 2^24 stored entries: a caller that reads the workspace must not expect them)
+  const c_int *Ap = (m > 0 && data->A) ? (const c_int *)data->A->p : nullptr, *Qp = (const c_int *)data->Q->p;
+  if ((size_t)(Ap ? Ap[n] : 0) + (size_t)Qp[n] <= (size_t)1 << 24 && data->A) {
     work->data->A = csc_copy_host(data->A); work->data->A->stype = 0;
     work->data->Q = csc_copy_host(data->Q);
   }

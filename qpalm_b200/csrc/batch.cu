@@ -845,6 +845,7 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
   st.sigma_max = s->sigma_max; st.sigma_init = s->sigma_init; st.gamma_init = s->gamma_init; st.gamma_upd = s->gamma_upd;
   st.gamma_max = s->gamma_max; st.max_rank_update_fraction = s->max_rank_update_fraction; st.sqrt_sigma_max = sqrt(s->sigma_max);
   st.data_c = shared->c;
+  { const char *u = getenv("QPALM_B200_BATCH_UPDOWN"); st.batch_updown = u ? atoi(u) : 1; }
   if (s->scaling) {   // Ruiz on the shared matrices; the cost scaling c is per instance (applied on the fly)
     double cc;
     if (engine_ruiz_scale(e, (int)s->scaling, &cc)) { engine_destroy(e); delete B; return nullptr; }
@@ -1043,12 +1044,15 @@ extern "C" int qpalm_b200_batch_solve(QPALMB200Batch *B, c_int nb, const c_float
 
 // totals over the instances of the last download: [0] inner iterations, [1] outer iterations, [2] refactorisations,
 // [3] sum of |J| over them, [4] engine used (1 lock-step, 2 persistent)
-extern "C" int qpalm_b200_batch_stats(QPALMB200Batch *B, c_int nb, double *out5) {
+extern "C" int qpalm_b200_batch_stats(QPALMB200Batch *B, c_int nb, double *out8) {
   if (!B || nb <= 0 || nb > B->nb_max) return 1;
   QB_CUDA_TRY(cudaMemcpy(B->ctl_host.data(), B->ctl, sizeof(BCtl) * (size_t)nb, cudaMemcpyDeviceToHost));
-  double a = 0, o = 0, r = 0, j = 0;
-  for (c_int b = 0; b < nb; b++) { const BCtl &c = B->ctl_host[b]; a += c.n_inner; o += c.iter_out; r += c.n_refac; j += (double)c.refac_J; }
-  out5[0] = a; out5[1] = o; out5[2] = r; out5[3] = j; out5[4] = B->last_engine;
+  double a = 0, o = 0, r = 0, j = 0, u = 0, ur = 0, uf = 0;
+  for (c_int b = 0; b < nb; b++) {
+    const BCtl &c = B->ctl_host[b];
+    a += c.n_inner; o += c.iter_out; r += c.n_refac; j += (double)c.refac_J; u += c.n_updown; ur += (double)c.updown_ranks; uf += c.n_updown_fail;
+  }
+  out8[0] = a; out8[1] = o; out8[2] = r; out8[3] = j; out8[4] = B->last_engine; out8[5] = u; out8[6] = ur; out8[7] = uf;
   return 0;
 }
 

@@ -15,12 +15,15 @@ struct BCtl {   // per-instance control state (device resident)
   double eps_pri, eps_dua, eps_dua_in, objective, beta;
   int n_inner, n_refac;          // executed inner steps / Newton refactorisations (roofline byte model)
   long long refac_J;             // sum of |J| over the refactorisations
+  int n_updown, n_updown_fail;   // rank-k update / downdate sweeps taken instead of a refactorisation (and downdates that lost definiteness)
+  long long updown_ranks;        // sum of ranks over the sweeps
 };
 
 struct BSet {   // settings the device needs (copied by value into kernels)
   int max_iter, inner_max_iter, proximal, scaling, reset_newton_iter, max_rank_update;
   double eps_abs, eps_rel, eps_abs_in, eps_rel_in, rho, eps_prim_inf, eps_dual_inf, theta, delta, sigma_max, sigma_init;
   double gamma_init, gamma_upd, gamma_max, max_rank_update_fraction, sqrt_sigma_max, data_c;
+  int batch_updown;              // persistent engine: take rank updates where the reference does (QPALM_B200_BATCH_UPDOWN=0 disables)
 };
 }  // namespace qb
 

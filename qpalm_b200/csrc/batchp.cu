@@ -17,7 +17,9 @@
 //   H is kept per instance and updated incrementally (+ entering / - leaving / +- sigma changes) by an in-CTA
 //   rank-32-chunk SYRK, L <- chol(H + beta I) by an in-CTA right-looking blocked Cholesky (32-column panels: diagonal
 //   block in one warp's registers, panel solve one row per thread, 4 x 4 register-blocked trailing update), then two
-//   blocked triangular solves.  All arithmetic is fp64 FMA (on B200 the DMMA and DFMA peaks coincide).
+//   blocked triangular solves.  When the active set changes by at most min(0.1 (n + m), max_rank_update) rows and the
+//   factor is current, the factor is UPDATED in place instead (cta_updown_sweep: <= 8 ranks per sweep, entering rows
+//   before leaving rows), exactly where the reference takes cholmod_updown (newton.c:98-108).  All arithmetic is fp64 FMA.
 #include "batch.cuh"
 #include <math.h>
 #include <string.h>
@@ -97,7 +99,7 @@ struct Args {
   long long *prof;   // optional [nb][16] per-phase clock64 totals (QPALM_B200_BATCH_PROF=1)
 };
 
-struct Flags { int outer, sigma, inner, refac, factor, fq, boost, done; };
+struct Flags { int outer, sigma, inner, refac, factor, fq, boost, done, updown; };
 
 struct Smem {
   unsigned char *u;      // union region: sort buffers / panel
@@ -310,7 +312,7 @@ __device__ __noinline__ void p_res_n(const Args &P, int b, double *scratch) {
 __device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
   const BSet &st = P.st;
   const int n = P.n, m = P.m;
-  f.outer = f.sigma = f.inner = f.refac = f.factor = f.fq = f.boost = f.done = 0;
+  f.outer = f.sigma = f.inner = f.refac = f.factor = f.fq = f.boost = f.done = f.updown = 0;
   BCtl c = P.ctl[b];
   const double *h = P.scal + (size_t)b * S_COUNT;
   const double cinv = st.scaling ? c.cinv : 1.0;
@@ -371,7 +373,9 @@ __device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
     const double rank_limit = fmin(st.max_rank_update_fraction * (double)(n + m), (double)st.max_rank_update);
     c.scratch = 0;
     if ((c.reset_newton && na) || (double)(ne + nl) > rank_limit) { f.refac = 1; f.factor = 1; c.scratch = c.reset_newton || !c.H_valid; }
-    else if (na) { if (ne + nl > 0) { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
+    else if (na) {   // newton.c:103-108: rank update of the factor (entering rows, then leaving rows)
+      if (ne + nl > 0) { if (st.batch_updown) f.updown = 1; else { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
+    }
     else { f.fq = 1; f.factor = 1; }
     c.reset_newton = 0;
     c.n_inner++;
@@ -728,6 +732,160 @@ __device__ __forceinline__ void cta_syrk_list(double *dst, int ld, int n, const 
     cta_rank_update_lower(dst, ld, nullptr, 0, 0.0, 0.0, false, 0, n, S.panel, 0, w, sign);
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rank-k update / downdate of the instance's factor inside the CTA -- the cholmod_updown replacement of the batch engine
+// (ldlupdate_entering_constraints / ldldowndate_leaving_constraints, src/solver_interface.c:407-441; recurrence of
+// Modify/t_cholmod_updown_numkr.c:289-376 restated for L L').  <= KU ranks per sweep, entering rows (+) before leaving (-).
+//
+// Per column j with pivot d = l_jj^2 and, per rank r, the carried alpha_r and the current w_r[j]:
+//     d_{r+1} = d_r + s_r w_r[j]^2 / alpha_r          gamma_r = -s_r w_r[j] / (alpha_r d_{r+1})        alpha_r <- alpha_r d_{r+1} / d_r
+// and for the rows below:  t = l_ij / l_jj;  { w_r[i] -= w_r[j] t;  t -= gamma_r w_r[i] } over r;  l_ij = t sqrt(d_k).
+// The chain over the ranks of one column only ever ADDS (s_r w^2 / alpha_r are known up front), so lane r of warp 0 owns
+// rank r, the d_r come out of one warp prefix sum and each lane pays a single division: the serial cost per column does
+// not grow with the rank.  The sweep walks 16-column panels staged in shared memory: warp 0 runs the recurrence on the
+// 16 x 16 diagonal block (its rows of W in registers) and leaves the column coefficients in shared memory, then every thread
+// transforms one row below the block.
+// ------------------------------------------------------------------------------------------------
+constexpr int KU = 8, UW = 16;
+static_assert((UW + KU) * LDP * sizeof(double) <= kUnionBytes, "update panel + W block must fit the union region");
+
+struct UdCoef {   // in S.vs
+  double winv[UW], lnew[UW], wj[UW][KU], gam[UW][KU], ialpha[KU], wjs[KU];
+};
+static_assert(sizeof(UdCoef) <= sizeof(double) * VS_LEN, "update coefficients must fit the staged-vector buffer");
+
+// one sweep: L <- chol(L L' + sum_{r < kpos} w_r w_r' - sum_{kpos <= r < k} w_r w_r'),  w_r = wgt[r] * A'[:, list[r]]
+__device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *rdiag_g, const double *__restrict__ At,
+                                              const int *__restrict__ list, const double *__restrict__ wgt, int k, int kpos, const Smem &S, int *info) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *Pn = S.panel, *Wm = S.panel + UW * LDP;
+  UdCoef &cf = *reinterpret_cast<UdCoef *>(S.vs);
+  for (int idx = tid; idx < KU * n; idx += NT) {   // gather the rows (zero columns beyond k)
+    const int r = idx / n, i = idx - r * n;
+    Wm[r * LDP + i] = (r < k) ? wgt[r] * At[(size_t)i + (size_t)n * list[r]] : 0.0;
+  }
+  if (tid < KU) cf.ialpha[tid] = 1.0;
+  for (int idx = tid; idx < UW * KU; idx += NT) { cf.wj[0][idx] = 0.0; cf.gam[0][idx] = 0.0; }
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += UW) {
+    const int w = (n - k0 < UW) ? n - k0 : UW, rows = n - k0;
+    for (int idx = tid; idx < w * rows; idx += NT) {   // panel load, rows fastest (coalesced)
+      const int t = idx / rows, r = idx - t * rows;
+      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {   // the recurrence on the diagonal block: lane = block row (w of them) AND lane = rank (k of them)
+      double wl[KU];
+#pragma unroll
+      for (int r = 0; r < KU; r++) wl[r] = (lane < w) ? Wm[r * LDP + k0 + lane] : 0.0;
+      double ial = (lane < KU) ? cf.ialpha[lane] : 1.0;
+      const double sg = (lane < kpos) ? 1.0 : -1.0;
+      bool bad = false;
+      __syncwarp();
+      for (int j = 0; j < w; j++) {
+        if (lane == j) {
+#pragma unroll
+          for (int r = 0; r < KU; r++) cf.wjs[r] = wl[r];
+        }
+        const double ljj = Pn[j * LDP + j];
+        __syncwarp();
+        const double wj = (lane < k) ? cf.wjs[lane] : 0.0;
+        const double c = sg * wj * wj * ial;
+        double incl = c;
+#pragma unroll
+        for (int off = 1; off < KU; off <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += up;
+        }
+        const double d0 = ljj * ljj;
+        const double dnext = d0 + incl, dprev = d0 + (incl - c);
+        if (lane < k && !(dnext > 0.0)) bad = true;
+        const double q = ial / dnext;
+        const double gam = -sg * wj * q;
+        ial = dprev * q;
+        const double dfin = __shfl_sync(0xffffffffu, dnext, k - 1);
+        const double lnew = sqrt(dfin), winv = 1.0 / ljj;
+        if (lane < k) { cf.wj[j][lane] = wj; cf.gam[j][lane] = gam; }
+        if (lane == 0) { cf.winv[j] = winv; cf.lnew[j] = lnew; }
+        __syncwarp();
+        double t = Pn[j * LDP + lane] * winv;
+        if (lane > j) {
+#pragma unroll
+          for (int r = 0; r < KU; r++) {
+            wl[r] = fma(-cf.wj[j][r], t, wl[r]);
+            t = fma(-cf.gam[j][r], wl[r], t);
+          }
+        }
+        if (lane > j && lane < w) Pn[j * LDP + lane] = t * lnew;
+        else if (lane == j) Pn[j * LDP + j] = lnew;
+        __syncwarp();
+      }
+      if (lane < KU) cf.ialpha[lane] = ial;
+      if (__any_sync(0xffffffffu, bad) && lane == 0) *info = 1;
+    }
+    __syncthreads();
+    for (int rr = w + tid; rr < rows; rr += NT) {   // rows below the block: one row per thread
+      double wv[KU];
+#pragma unroll
+      for (int r = 0; r < KU; r++) wv[r] = Wm[r * LDP + k0 + rr];
+      for (int c = 0; c < w; c++) {
+        double t = Pn[c * LDP + rr] * cf.winv[c];
+#pragma unroll
+        for (int r = 0; r < KU; r++) {
+          wv[r] = fma(-cf.wj[c][r], t, wv[r]);
+          t = fma(-cf.gam[c][r], wv[r], t);
+        }
+        Pn[c * LDP + rr] = t * cf.lnew[c];
+      }
+#pragma unroll
+      for (int r = 0; r < KU; r++) Wm[r * LDP + k0 + rr] = wv[r];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * rows; idx += NT) {
+      const int t = idx / rows, r = idx - t * rows;
+      if (r >= t) L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] = Pn[t * LDP + r];
+    }
+    if (tid < w) rdiag_g[k0 + tid] = 1.0 / cf.lnew[tid];
+    __syncthreads();
+  }
+}
+
+// ordered lists of the entering (candidate active, not in the factor) and leaving rows, entering first, weights sqrt(sigma):
+// list_pos[0 .. ne + nl), w_pos likewise (set_entering_leaving_constraints, newton.c:134-149).  Returns counts through ctl.npos / nneg.
+__device__ __noinline__ void p_updown_lists(const Args &P, int b) {
+  __shared__ int warp_cnt0[NW], warp_cnt1[NW];
+  __shared__ int base0, base1;
+  const int m = P.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t om = (size_t)b * m;
+  if (tid == 0) { base0 = 0; base1 = 0; }
+  __syncthreads();
+  for (int start = 0; start < m; start += NT) {
+    const int i = start + tid;
+    bool p0 = false, p1 = false;
+    if (i < m) {
+      const int a = P.active_cand[om + i], o = P.active_old[om + i];
+      p0 = a && !o; p1 = !a && o;
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+    if (lane == 0) { warp_cnt0[warp] = __popc(b0); warp_cnt1[warp] = __popc(b1); }
+    __syncthreads();
+    int off0 = base0, off1 = base1;
+    for (int w = 0; w < warp; w++) { off0 += warp_cnt0[w]; off1 += warp_cnt1[w]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if (p0) P.list_pos[om + off0 + __popc(b0 & lt)] = i;
+    if (p1) P.list_neg[om + off1 + __popc(b1 & lt)] = i;
+    __syncthreads();
+    if (tid == 0) { int t0 = 0, t1 = 0; for (int w = 0; w < NW; w++) { t0 += warp_cnt0[w]; t1 += warp_cnt1[w]; } base0 += t0; base1 += t1; }
+    __syncthreads();
+  }
+  const int ne = base0, nl = base1;
+  __syncthreads();
+  for (int q = tid; q < nl; q += NT) P.list_pos[om + ne + q] = P.list_neg[om + q];   // append the leaving rows
+  __syncthreads();
+  for (int q = tid; q < ne + nl; q += NT) P.w_pos[om + q] = P.sqrt_sigma[om + P.list_pos[om + q]];
+  if (tid == 0) { BCtl &c = P.ctl[b]; c.npos = ne; c.nneg = nl; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1118,10 +1276,31 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
       PH(4);
       // ---- inner step ----
       if (f.inner) {
-        p_lists(P, b, f.refac);
+        int refac = f.refac, factor = f.factor;
+        if (f.updown) {   // rank update of the factor instead of a refactorisation (newton.c:103-108)
+          p_updown_lists(P, b);
+          if (tid == 0) s_info = 0;
+          __syncthreads();
+          const int ne = P.ctl[b].npos, nl = P.ctl[b].nneg;
+          for (int off = 0; off < ne + nl; off += KU) {
+            const int k = (ne + nl - off < KU) ? ne + nl - off : KU;
+            const int kpos = (ne - off < 0) ? 0 : ((ne - off < k) ? ne - off : k);
+            cta_updown_sweep(Lb, ld, n, rdg, P.At, P.list_pos + om + off, P.w_pos + om + off, k, kpos, S, &s_info);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            BCtl &c = P.ctl[b];
+            c.n_updown += (ne + nl + KU - 1) / KU; c.updown_ranks += ne + nl;
+            if (s_info) { c.n_updown_fail++; c.scratch = !c.H_valid; c.n_refac++; c.refac_J += c.nb_active; }
+          }
+          if (s_info) { refac = 1; factor = 1; }   // a downdate lost definiteness: rebuild the factor from H
+          __syncthreads();
+          PH(14);
+        }
+        p_lists(P, b, refac);
         __syncthreads();
         PH(5);
-        if (f.refac) {
+        if (refac) {
           const BCtl c = P.ctl[b];
           if (c.scratch) {
             for (int idx = tid; idx < n * n; idx += NT) {
@@ -1137,14 +1316,14 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
         PH(6);
         for (int i = tid; i < n; i += NT) S.v[i] = P.dphi[on + i] * -1;
         __syncthreads();
-        if (f.factor) {
+        if (factor) {
           const double beta = P.ctl[b].beta;
           if (tid == 0) s_info = 0;
           cta_potrf(Lb, ld, f.fq ? P.Qs : Hb, f.fq ? n : ld, f.fq ? P.ctl[b].c : 1.0, beta, n, rdg, S, &s_info, true,
                     P.prof ? P.prof + (size_t)b * 32 : nullptr);
         }
         PH(7);
-        cta_chol_solve(Lb, ld, n, rdg, S, f.factor != 0);
+        cta_chol_solve(Lb, ld, n, rdg, S, factor != 0);
         for (int i = tid; i < n; i += NT) P.d[on + i] = S.v[i];
         for (int i = tid; i < m; i += NT) P.active_old[om + i] = P.active[om + i];
         __syncthreads();

@@ -7,6 +7,7 @@
 #include "engine.cuh"
 #include <vector>
 #include <chrono>
+#include <thread>
 #include <math.h>
 #include <string.h>
 
@@ -157,9 +158,16 @@ __global__ void __launch_bounds__(256) k_csr_spmv(int rows, const int *__restric
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int b = p[row], en = p[row + 1];
-  double acc = 0.0;
-  for (int k = b + lane; k < en; k += 32) acc = fma(v[k], __ldg(x + ci[k]), acc);
-  acc = warp_sum(acc);
+  // 128-bit value loads / 64-bit index loads on even-aligned pairs (the arrays carry two elements of padding, the first and
+  // last pair of a row are masked); two accumulators per lane, fixed order
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int k = (b & ~1) + 2 * lane; k < en; k += 64) {
+    const double2 vv = *reinterpret_cast<const double2 *>(v + k);
+    const int2 cc = *reinterpret_cast<const int2 *>(ci + k);
+    if (k >= b) acc0 = fma(vv.x, __ldg(x + cc.x), acc0);
+    if (k + 1 < en) acc1 = fma(vv.y, __ldg(x + cc.y), acc1);
+  }
+  const double acc = warp_sum(acc0 + acc1);
   if (lane == 0) y[row] = acc;
 }
 // dense, column dots: y[k] = sum_i M[i + ld*k] x[i]; one warp per column, 4 independent accumulators
@@ -1495,15 +1503,65 @@ static int up(T **dst, const T *src, size_t count) {
 static int upload_sparse(SparseDev *S, int rows, int cols, const int *p, const int *i, const double *x) {
   S->rows = rows; S->cols = cols; S->nnz = p[rows];
   if (int r = up(&S->p, p, (size_t)rows + 1)) return r;
-  if (int r = up(&S->i, i, (size_t)S->nnz)) return r;
-  if (int r = up(&S->x, x, (size_t)S->nnz)) return r;
-  return 0;
+  // two elements of zero padding: the SpMV kernel reads aligned pairs (masked lanes may touch the element after the last)
+  {
+    const size_t cnt = (size_t)S->nnz;
+    if (int r = dev_alloc((void **)&S->i, sizeof(int) * (cnt + 2))) return r;
+    if (int r = dev_alloc((void **)&S->x, sizeof(double) * (cnt + 2))) return r;
+    QB_CUDA_TRY(cudaMemset(S->i + cnt, 0, sizeof(int) * 2));
+    QB_CUDA_TRY(cudaMemset(S->x + cnt, 0, sizeof(double) * 2));
+    if (cnt) {
+      QB_CUDA_TRY(cudaMemcpy(S->i, i, sizeof(int) * cnt, cudaMemcpyHostToDevice));
+      QB_CUDA_TRY(cudaMemcpy(S->x, x, sizeof(double) * cnt, cudaMemcpyHostToDevice));
+    }
+    return 0;
+  }
+}
+
+// The dense fast paths upload the value array verbatim, which is only right when the column listings are complete AND in
+// ascending row order (callers may pass sorted = 0, and a duplicate entry can make the count match by accident): check the
+// row indices before trusting them.  Memory-bound scan, a few host threads.
+static bool csc_is_full_dense(int n, int m, const long long *Ap, const long long *Ai) {
+  for (int j = 0; j <= n; j++) if (Ap[j] != (long long)j * m) return false;
+  const int nt = (n >= 64 && (long long)n * m > (1 << 22)) ? 8 : 1;
+  std::vector<int> ok(nt, 1);
+  auto scan = [&](int t) {
+    for (int j = t; j < n && ok[t]; j += nt) {
+      const long long *col = Ai + (size_t)j * m;
+      long long bad = 0;
+      for (int i = 0; i < m; i++) bad |= col[i] ^ (long long)i;
+      if (bad) ok[t] = 0;
+    }
+  };
+  if (nt == 1) scan(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(scan, t); for (auto &x : th) x.join(); }
+  for (int v : ok) if (!v) return false;
+  return true;
+}
+static bool csc_is_packed_lower(int n, const long long *Qp, const long long *Qi) {
+  long long pos = 0;
+  for (int j = 0; j < n; j++) {
+    if (Qp[j] != pos) return false;
+    const long long *col = Qi + pos;
+    long long bad = 0;
+    for (int i = j; i < n; i++) bad |= col[i - j] ^ (long long)i;
+    if (bad) return false;
+    pos += n - j;
+  }
+  return Qp[n] == pos;
 }
 
 int engine_create(Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
                   const long long *Qp, const long long *Qi, const double *Qx,
                   const double *q, const double *bmin, const double *bmax, bool need_LQ, int newton_override) {
   *out = nullptr;
+  {   // the device forms use int32 indices: refuse what does not fit instead of overflowing
+    const long long nnzA_ = m > 0 ? Ap[n] : 0, nnzQ_ = Qp[n];
+    if (nnzA_ > 2147483647LL || 2 * nnzQ_ > 2147483647LL) {
+      fprintf(stderr, "[qpalm_b200] nnz(A) = %lld / nnz(Q) = %lld exceed the int32 index range of the device storage\n", nnzA_, nnzQ_);
+      return 3;
+    }
+  }
   int ndev = 0;
   QB_CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (ndev <= 0) { fprintf(stderr, "[qpalm_b200] no CUDA device: this library has no CPU fallback\n"); return 1; }
@@ -1542,13 +1600,13 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     const int ml = e->m_loc, lo = e->m_lo;
     double *tmp = nullptr;
     if (int r = dev_alloc((void **)&tmp, sizeof(double) * (size_t)(ml ? ml : 1) * n)) return r;
-    if (ml > 0 && nnzA == (long long)m * n) {   // complete dense CSC: rows lo..lo+ml-1 of every column
+    if (ml > 0 && nnzA == (long long)m * n && csc_is_full_dense(n, m, Ap, Ai)) {   // complete dense CSC in row order: rows lo..lo+ml-1 of every column
       QB_CUDA_TRY(cudaMemcpy2D(tmp, sizeof(double) * (size_t)ml, Ax + lo, sizeof(double) * (size_t)m, sizeof(double) * (size_t)ml,
                                (size_t)n, cudaMemcpyHostToDevice));
     } else if (ml > 0) {
       double *hd = (double *)calloc((size_t)ml * n, sizeof(double));
       for (int j = 0; j < n; j++)
-        for (long long k = Ap[j]; k < Ap[j + 1]; k++) { const long long r = Ai[k] - lo; if (r >= 0 && r < ml) hd[(size_t)r + (size_t)ml * j] = Ax[k]; }
+        for (long long k = Ap[j]; k < Ap[j + 1]; k++) { const long long r = Ai[k] - lo; if (r >= 0 && r < ml) hd[(size_t)r + (size_t)ml * j] += Ax[k]; }   // duplicates sum, as in the CSR path
       QB_CUDA_TRY(cudaMemcpy(tmp, hd, sizeof(double) * (size_t)ml * n, cudaMemcpyHostToDevice));
       free(hd);
     }
@@ -1580,7 +1638,7 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   e->Q_dense = !force_sparse && (double)nnzL >= 0.25 * 0.5 * (double)n * ((double)n + 1.0);
   if (e->Q_dense) {
     if (int r = dev_alloc((void **)&e->Qd, sizeof(double) * (size_t)n * n)) return r;
-    if (nnzL == (long long)n * (n + 1) / 2 && Qp[n] == nnzL) {   // packed dense lower triangle: expand on the device
+    if (nnzL == (long long)n * (n + 1) / 2 && Qp[n] == nnzL && csc_is_packed_lower(n, Qp, Qi)) {   // packed dense lower triangle in row order: expand on the device
       double *tmp = nullptr;
       if (int r = up(&tmp, Qx, (size_t)nnzL)) return r;
       dim3 grid(cdiv(n, 256), n);
@@ -1590,7 +1648,8 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     } else {
       double *hd = (double *)calloc((size_t)n * n, sizeof(double));
       for (int j = 0; j < n; j++) for (long long k = Qp[j]; k < Qp[j + 1]; k++) if (Qi[k] >= j) {
-        hd[(size_t)Qi[k] + (size_t)n * j] = Qx[k]; hd[(size_t)j + (size_t)n * Qi[k]] = Qx[k];
+        hd[(size_t)Qi[k] + (size_t)n * j] += Qx[k];          // duplicates sum, as in the CSR path
+        if (Qi[k] != j) hd[(size_t)j + (size_t)n * Qi[k]] += Qx[k];
       }
       QB_CUDA_TRY(cudaMemcpy(e->Qd, hd, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
       free(hd);

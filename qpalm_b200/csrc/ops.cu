@@ -449,6 +449,31 @@ extern "C" int qpalm_b200_bench_updown(c_int n_, c_int k_, c_int reps, double *m
   return rc ? rc : hinfo;
 }
 
+// sparse products at a caller-given shape (C1 / C2 of BASELINE.json): ms per A x, A' y and Q x through the solver's kernels.
+// out3 = {ms A x, ms A' y, ms Q x}; algorithmic bytes per product are 12 nnz + 4 (rows + 1) + 8 (rows + cols).
+extern "C" int qpalm_b200_bench_spmv(const solver_sparse *A, const solver_sparse *Q, c_int reps, double *out3, c_int *nnz3) {
+  Engine *e = nullptr;
+  const int n = (int)Q->ncol, m = (int)A->nrow;
+  if (int rc = make_engine(&e, n, m, A, Q, false, 2)) return rc;
+  if (e->A_dense || e->Q_dense) { engine_destroy(e); return 7; }
+  vec_set(e, e->x, 1.0, n); vec_set(e, e->y, 1.0, m);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int which = 0; which < 3; which++) {
+    auto run = [&]() { return which == 0 ? spmv_A(e, e->x, e->Ax) : (which == 1 ? spmv_At(e, e->y, e->Aty) : spmv_Q(e, e->x, e->Qx)); };
+    run();
+    cudaEventRecord(a, e->stream);
+    for (int r = 0; r < reps; r++) run();
+    cudaEventRecord(b, e->stream);
+    QB_CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    out3[which] = ms / (reps > 0 ? reps : 1);
+  }
+  nnz3[0] = e->A_csr.nnz; nnz3[1] = e->A_csc.nnz; nnz3[2] = e->Q_csr.nnz;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  engine_destroy(e);
+  return 0;
+}
+
 // stage clocks of the chain CTA of one sweep (panels 100 and 101): out32 receives up to 32 clock64 stamps
 extern "C" int qpalm_b200_bench_updown_clocks(c_int n_, c_int k_, long long *out32) {
   const int n = round_up((int)n_, 128), k = (int)k_;
@@ -510,6 +535,45 @@ extern "C" int qpalm_b200_bench_dmma_peak(double *tflops_out) {
     QB_CUDA_TRY(cudaEventSynchronize(b));
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
     const double flops = (double)grid * 8 /*warps*/ * iters * 16.0 * 512.0;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  *tflops_out = best;
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(sink);
+  return 0;
+}
+
+// scalar FP64 FMA issue-rate peak (register-resident DFMA chains, 16 independent accumulators per thread): the bound of every
+// kernel that does its arithmetic with plain fma() instead of DMMA.  warps_per_sm: resident warps per SM during the probe.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double *sink) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-9 + i * 1e-7;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += acc[i];
+  if (s == 123.456) sink[0] = s;
+}
+extern "C" int qpalm_b200_bench_dfma_peak(double *tflops_out) {
+  double *sink = nullptr;
+  QB_CUDA_TRY(cudaMalloc(&sink, 8));
+  cudaStream_t s; QB_CUDA_TRY(cudaStreamCreate(&s));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 8192, grid = 148 * 8;
+  QB_LAUNCH(k_dfma_peak, grid, 256, 0, s, 64, sink);
+  double best = 0;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(a, s);
+    QB_LAUNCH(k_dfma_peak, grid, 256, 0, s, iters, sink);
+    cudaEventRecord(b, s);
+    QB_CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    const double flops = (double)grid * 256 * iters * 16.0 * 2.0;
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (tf > best) best = tf;
   }

@@ -339,6 +339,15 @@ extern "C" int qpalm_b200_qps_read(const char *path, QPALMData **data_out, char 
     }
     Qp[n] = (int64_t)k;
   }
+  // Entries come out in FILE order (that is what the reference reader produces and what the parity tests pin), so a column
+  // is sorted only if the file listed it that way: say so truthfully instead of claiming sorted = 1.
+  for (solver_sparse *M : {d->A, d->Q}) {
+    const int64_t *Mp = (const int64_t *)M->p, *Mi = (const int64_t *)M->i;
+    int sorted = 1;
+    for (size_t j = 0; j < M->ncol && sorted; j++)
+      for (int64_t k = Mp[j] + 1; k < Mp[j + 1]; k++) if (Mi[k] <= Mi[k - 1]) { sorted = 0; break; }
+    M->sorted = sorted;
+  }
   if (name_out && name_len) { strncpy(name_out, P.name.c_str(), name_len - 1); name_out[name_len - 1] = 0; }
   *data_out = d;
   return 0;

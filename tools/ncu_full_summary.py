@@ -30,5 +30,30 @@ def main(path):
                     print(f"  {h:85s} {v:16.2f} %")
 
 
+def traffic_json(path, kernel, batch, source):
+    """append {batch, dram_bytes, source} for `kernel` to profiles/ncu_traffic.json (bench.py reads roofline.traffic from it)"""
+    import json
+    import os
+    rows = [r for r in csv.reader(open(path)) if r]
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total = 0.0
+    for vals in rows[2:3]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k]
+            total += float(v.replace(",", "")) * scale.get(u, 1.0)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    db = json.load(open(out)) if os.path.exists(out) else {}
+    ents = [e for e in db.get(kernel, []) if int(e["batch"]) != int(batch)]
+    ents.append({"batch": int(batch), "dram_bytes": total, "source": source})
+    db[kernel] = ents
+    json.dump(db, open(out, "w"), indent=1)
+    print("wrote", out, kernel, batch, total)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic-json":
+        traffic_json(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5])
+    else:
+        main(sys.argv[1])
