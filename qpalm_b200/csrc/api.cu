@@ -160,6 +160,14 @@ extern "C" QPALMWorkspace *qpalm_setup(const QPALMData *data, const QPALMSetting
 #undef VM
 #undef V2M
   work->initialized = FALSE;
+  {   // the reference wraps these work vectors in cholmod_dense headers (qpalm.c:190-250) and its test-suite reaches them
+      // through work->solver->Qd etc.: same layout (cholmod_core.h:1894-1905), the x pointer aliases the host mirror
+    struct DenseHdr { size_t nrow, ncol, nzmax, d; void *x, *z; int xtype, dtype; };
+    auto wrap = [](c_float *x, size_t len) { DenseHdr *h = (DenseHdr *)calloc(1, sizeof(DenseHdr)); h->nrow = len; h->ncol = 1; h->nzmax = len; h->d = len; h->x = x; h->xtype = 1; return (void *)h; };
+    work->solver->neg_dphi = wrap(work->neg_dphi, n); work->solver->d = wrap(work->d, n); work->solver->Qd = wrap(work->Qd, n);
+    work->solver->Ad = wrap(work->Ad, m); work->solver->yh = wrap(work->yh, m); work->solver->Atyh = wrap(work->Atyh, n);
+    work->solver->E_temp = wrap(work->E_temp, m); work->solver->D_temp = wrap(work->D_temp, n);
+  }
   work->solver->factorization_method = FACTORIZE_SCHUR;   // solver_interface.c:72-73
   work->solver->active_constraints = (c_int *)calloc(m + 1, sizeof(c_int));
   work->solver->active_constraints_old = (c_int *)calloc(m + 1, sizeof(c_int));
@@ -745,7 +753,12 @@ extern "C" void qpalm_cleanup(QPALMWorkspace *work) {   // qpalm.c:874-1096
   FR(neg_dphi); FR(d); FR(Qd); FR(Ad); FR(yh); FR(Atyh); FR(D_temp); FR(E_temp);
 #undef FR
   free(work->settings);
-  if (work->solver) { free(work->solver->active_constraints); free(work->solver->active_constraints_old); free(work->solver->enter); free(work->solver->leave); free(work->solver); }
+  if (work->solver) {
+    free(work->solver->active_constraints); free(work->solver->active_constraints_old); free(work->solver->enter); free(work->solver->leave);
+    free(work->solver->neg_dphi); free(work->solver->d); free(work->solver->Qd); free(work->solver->Ad); free(work->solver->yh);
+    free(work->solver->Atyh); free(work->solver->E_temp); free(work->solver->D_temp);
+    free(work->solver);
+  }
   if (work->solution) { free(work->solution->x); free(work->solution->y); free(work->solution); }
   free(work->timer); free(work->info); free(work);
 }

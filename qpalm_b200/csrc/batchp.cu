@@ -752,7 +752,7 @@ constexpr int KU = 8, UW = 16;
 static_assert((UW + KU) * LDP * sizeof(double) <= kUnionBytes, "update panel + W block must fit the union region");
 
 struct UdCoef {   // in S.vs
-  double winv[UW], lnew[UW], wj[UW][KU], gam[UW][KU], ialpha[KU], wjs[KU];
+  double winv[UW], lnew[UW], wj[UW][KU], gam[UW][KU], ialpha[KU], wrow[32][KU + 1];
 };
 static_assert(sizeof(UdCoef) <= sizeof(double) * VS_LEN, "update coefficients must fit the staged-vector buffer");
 
@@ -783,15 +783,20 @@ __device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *
       double ial = (lane < KU) ? cf.ialpha[lane] : 1.0;
       const double sg = (lane < kpos) ? 1.0 : -1.0;
       bool bad = false;
+      // off the chain: the old pivots are not touched before their own column, so 1 / l_jj and l_jj^2 of all 16 columns are
+      // formed up front (lane = column), and the new pivots sqrt(d) and the column scaling wait until after the loop
+      const double ldiag = (lane < w) ? Pn[lane * LDP + lane] : 1.0;
+      const double winv_l = 1.0 / ldiag, d0_l = ldiag * ldiag;
+      double dfin_l = 1.0;
       __syncwarp();
+      // The loop body has NO divergent region (a warp that splits pays the slow collective path on every later shuffle):
+      // every lane publishes its row of W each column, stale rows (<= j) keep computing on dead values, stores are predicated.
       for (int j = 0; j < w; j++) {
-        if (lane == j) {
 #pragma unroll
-          for (int r = 0; r < KU; r++) cf.wjs[r] = wl[r];
-        }
-        const double ljj = Pn[j * LDP + j];
+        for (int r = 0; r < KU; r++) cf.wrow[lane][r] = wl[r];
+        const double winv = __shfl_sync(0xffffffffu, winv_l, j), d0 = __shfl_sync(0xffffffffu, d0_l, j);
         __syncwarp();
-        const double wj = (lane < k) ? cf.wjs[lane] : 0.0;
+        const double wj = (lane < k) ? cf.wrow[j][lane & (KU - 1)] : 0.0;
         const double c = sg * wj * wj * ial;
         double incl = c;
 #pragma unroll
@@ -799,28 +804,35 @@ __device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *
           const double up = __shfl_up_sync(0xffffffffu, incl, off);
           if (lane >= off) incl += up;
         }
-        const double d0 = ljj * ljj;
         const double dnext = d0 + incl, dprev = d0 + (incl - c);
         if (lane < k && !(dnext > 0.0)) bad = true;
-        const double q = ial / dnext;
+        double q;   // ial / dnext: reciprocal seed + two Newton steps instead of the IEEE division subroutine
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(dnext));
+        q = fma(q, fma(-dnext, q, 1.0), q);
+        q = fma(q, fma(-dnext, q, 1.0), q);
+        q *= ial;
         const double gam = -sg * wj * q;
         ial = dprev * q;
         const double dfin = __shfl_sync(0xffffffffu, dnext, k - 1);
-        const double lnew = sqrt(dfin), winv = 1.0 / ljj;
+        if (lane == j) dfin_l = dfin;
         if (lane < k) { cf.wj[j][lane] = wj; cf.gam[j][lane] = gam; }
-        if (lane == 0) { cf.winv[j] = winv; cf.lnew[j] = lnew; }
         __syncwarp();
-        double t = Pn[j * LDP + lane] * winv;
-        if (lane > j) {
+        {
+          double t = Pn[j * LDP + (lane & (UW - 1))] * winv;
 #pragma unroll
           for (int r = 0; r < KU; r++) {
             wl[r] = fma(-cf.wj[j][r], t, wl[r]);
             t = fma(-cf.gam[j][r], wl[r], t);
           }
+          if (lane > j && lane < w) Pn[j * LDP + lane] = t;   // still unit-scaled; multiplied by the new pivot below
         }
-        if (lane > j && lane < w) Pn[j * LDP + lane] = t * lnew;
-        else if (lane == j) Pn[j * LDP + j] = lnew;
         __syncwarp();
+      }
+      const double lnew_l = sqrt(dfin_l);
+      if (lane < w) { cf.winv[lane] = winv_l; cf.lnew[lane] = lnew_l; Pn[lane * LDP + lane] = lnew_l; }
+      for (int j = 0; j < w; j++) {
+        const double lj = __shfl_sync(0xffffffffu, lnew_l, j);
+        if (lane > j && lane < w) Pn[j * LDP + lane] *= lj;
       }
       if (lane < KU) cf.ialpha[lane] = ial;
       if (__any_sync(0xffffffffu, bad) && lane == 0) *info = 1;
