@@ -211,6 +211,8 @@ typedef struct {
   int64_t sparse_levels;        /* assembly-tree levels = launches-in-sequence of one factorization pass */
   int64_t sigma_update_calls;   /* ldlupdate_sigma_changed equivalents taken (rank updates after a sigma change) */
   int64_t sigma_update_rank_sum;
+  int64_t kkt_factorizations;   /* > 0: the Newton steps went through the KKT path (kkt.cu); L S L' factorizations of the KKT matrix */
+  int64_t kkt_refinement_steps; /* iterative-refinement corrections applied after KKT solves (newton.c:57-90)                 */
 } QPALMB200Stats;
 int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *out);
 /* Selective per-kernel CUDA-event timing of the library's own launches (csrc/prof.cu): `patterns` is a comma-separated

@@ -130,7 +130,8 @@ class QPALMB200Stats(C.Structure):
                 ("device_ms_factor", C.c_double), ("device_ms_updown", C.c_double),
                 ("device_ms_total", C.c_double),
                 ("sparse_factor_nnz", C.c_int64), ("sparse_supernodes", C.c_int64), ("sparse_levels", C.c_int64),
-                ("sigma_update_calls", C.c_int64), ("sigma_update_rank_sum", C.c_int64)]
+                ("sigma_update_calls", C.c_int64), ("sigma_update_rank_sum", C.c_int64),
+                ("kkt_factorizations", C.c_int64), ("kkt_refinement_steps", C.c_int64)]
 
 
 # --------------------------------------------------------------------------------------------

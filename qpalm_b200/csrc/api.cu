@@ -180,9 +180,13 @@ extern "C" QPALMWorkspace *qpalm_setup(const QPALMData *data, const QPALMSetting
   work->info = (QPALMInfo *)calloc(1, sizeof(QPALMInfo));
 
   Engine *e = nullptr;
+  // factorization_method (constants.h: 0 KKT, 1 SCHUR, 2 KKT_OR_SCHUR): KKT is honoured (kkt.cu); SCHUR and the default
+  // KKT_OR_SCHUR take the Schur path like the reference's CHOLMOD build, except that sparse problems whose Schur complement
+  // fills in fall to the KKT system by the reference's own criterion (engine_create)
   int rc = engine_create(&e, (int)n, (int)m, (const long long *)data->A->p, (const long long *)data->A->i, (const double *)data->A->x,
                          (const long long *)data->Q->p, (const long long *)data->Q->i, (const double *)data->Q->x,
-                         data->q, data->bmin, data->bmax, settings->enable_dual_termination != 0);
+                         data->q, data->bmin, data->bmax, settings->enable_dual_termination != 0,
+                         settings->factorization_method == FACTORIZE_KKT ? 3 : (settings->factorization_method == FACTORIZE_SCHUR ? 5 : 0));
   if (rc) {
     QP_EPRINT("device engine creation failed (code %d); this library has no CPU fallback", rc);
     work->solver->LD = NULL;
@@ -190,6 +194,7 @@ extern "C" QPALMWorkspace *qpalm_setup(const QPALMData *data, const QPALMSetting
     return NULL;
   }
   work->solver->LD = e;
+  if (e->kkt) work->solver->factorization_method = FACTORIZE_KKT;
 
   if (settings->scaling) {
     work->scaling = (QPALMScaling *)calloc(1, sizeof(QPALMScaling));
@@ -393,6 +398,7 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 // against the last refactorisation.  Same matrix either way.
 static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0) return false;
+  if (e->kkt) return false;   // KKT path: a changed row is rewritten and the system refactorised (kkt.cu)
   const bool flow = !e->sp && e->updown_flow_ok && e->npad >= 256;   // one-launch dataflow sweep, <= 64 ranks each (updown_flow.cu)
   if (e->sh_world > 1 && !flow) return false;   // row-sharded: only the dataflow path allreduces the gathered rows
   if (!flow && k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
@@ -601,6 +607,21 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
       const double beta = st->proximal ? 1.0 / work->gamma : 0.0;
       const double rank_limit = c_min(st->max_rank_update_fraction * (double)(n + m), (double)st->max_rank_update);
       bool need_refactor = false, from_scratch = false, do_updown = false, factor_q = false;
+      if (e->kkt) {   // FACTORIZE_KKT branch of newton_set_direction (newton.c:22-95)
+        if (m > 0) cudaMemcpyAsync(e->active, e->active_cand, sizeof(int) * m, cudaMemcpyDeviceToDevice, e->stream);
+        const bool refac = sv->reset_newton || !e->kkt_valid || (ne + nl) > 0;
+        if (trace) fprintf(stderr, "[qpalm_b200 trace] iter %ld out %ld active %d enter %d leave %d -> KKT %s\n", (long)iter, (long)iter_out, na, ne, nl,
+                           refac ? "refactor" : "reuse factor");
+        if (refac) { kkt_refactor(e->kkt, e, beta); e->kkt_valid = true; pend.kind = 1; }
+        kkt_solve(e->kkt, e);
+        step_commit_active(e);
+        sv->reset_newton = FALSE;
+        step_linesearch(e, proximal, work->gamma);
+        step_update_iterate(e);
+        e->n_inner++;
+        e->alg_bytes += 2.0 * BA + BQ + 8.0 * (38.0 * m + 26.0 * n);
+        goto end_of_iteration;
+      }
       if ((sv->reset_newton && na) || (double)(ne + nl) > rank_limit) { need_refactor = true; from_scratch = sv->reset_newton != 0; }
       else if (na) {
         if (ne + nl > 0) { if (prefer_updown(e, ne + nl)) do_updown = true; else need_refactor = true; }
@@ -634,6 +655,7 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
         printf("%4ld | %.4e | %.4e | %.4e | %.4e \n", (long)iter, work->info->pri_res_norm, work->info->dua_res_norm, h[S_TAU], obj);
       }
     }
+  end_of_iteration:
     const c_float now = work->info->setup_time + toc(work);   // qpalm.c:680-708
     if (now > st->time_limit) {
       update_status(work->info, QPALM_TIME_LIMIT_REACHED);
@@ -771,7 +793,8 @@ extern "C" int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *
   out->refactor_active_sum = e->refactor_active_sum; out->updown_calls = e->n_updown; out->updown_rank_sum = e->updown_rank_sum;
   out->spmv_calls = e->n_spmv; out->algorithmic_bytes = e->alg_bytes; out->dense_flops = e->dense_flops;
   out->device_ms_factor = e->ms_factor; out->device_ms_updown = e->ms_updown; out->device_ms_total = e->ms_total;
-  out->sparse_factor_nnz = e->sp ? sparse_chol_info(e->sp)->nnzL : 0;
+  out->sparse_factor_nnz = e->kkt ? kkt_factor_nnz(e->kkt) : (e->sp ? sparse_chol_info(e->sp)->nnzL : 0);
+  out->kkt_factorizations = kkt_factor_count(e->kkt); out->kkt_refinement_steps = kkt_refine_count(e->kkt);
   out->sparse_supernodes = e->sp ? sparse_chol_info(e->sp)->nsuper : 0;
   out->sparse_levels = e->sp ? sparse_chol_info(e->sp)->nlevels : 0;
   out->sigma_update_calls = e->n_sigma_update; out->sigma_update_rank_sum = e->sigma_update_rank_sum;

@@ -53,5 +53,26 @@ __device__ __forceinline__ void fstep(double (&a)[SB], const int lane, double &d
   if constexpr (J + 1 < SB) fstep<J + 1>(a, lane, dl, dinv, badcol);
 }
 
+// Signed variant for quasi-definite blocks (the KKT factorization L S L', S = diag(+-1) known a priori: bit J of negmask set
+// means pivot J is negative).  Column J: l_JJ = sqrt(s_J p), L(i,J) = s_J a_iJ / l_JJ, trailing a_ic -= s_J (a_iJ / l_JJ)(a_cJ / l_JJ).
+template <int J>
+__device__ __forceinline__ void fstep_signed(double (&a)[SB], const int lane, double &dl, const unsigned negmask, int &badcol) {
+  const double sJ = ((negmask >> J) & 1u) ? -1.0 : 1.0;
+  const double pjj = sJ * __shfl_sync(FULL, a[J], J);
+  double ljj, inv;
+  sqrt_and_rcp(pjj, ljj, inv);
+  const double qi = a[J] * inv;
+  const double mq = -sJ * qi;
+#pragma unroll
+  for (int c = J + 1; c < SB; c++) {
+    const double qc = __shfl_sync(FULL, a[J], c) * inv;
+    a[c] = fma(mq, qc, a[c]);
+  }
+  if (!(pjj > 0.0) && badcol < 0) badcol = J;
+  a[J] = sJ * qi;
+  if (lane == J) dl = ljj;
+  if constexpr (J + 1 < SB) fstep_signed<J + 1>(a, lane, dl, negmask, badcol);
+}
+
 }  // namespace chol32
 }  // namespace qb

@@ -43,6 +43,8 @@ enum Scalar {
   S_COUNT = 64
 };
 
+struct KktEngine;            // kkt.cu: the KKT factorization path of the Newton step
+
 struct SparseDev {           // CSR or CSC, int32 indices
   int rows = 0, cols = 0; long long nnz = 0;
   int *p = nullptr, *i = nullptr; double *x = nullptr;
@@ -90,6 +92,10 @@ struct Engine {
   // sparse Newton system (sparse.cuh): supernodal factor instead of the dense H / L when the Schur complement stays sparse
   SparseChol *sp = nullptr;
   double *spL = nullptr, *spLQ = nullptr;   // numeric factors in the panel layout (Newton system; Q alone for the dual objective)
+  // KKT path (kkt.cu): when set, the Newton direction comes from the quasi-definite augmented system instead of the Schur
+  // complement; the factor is current for (active, sigma, gamma) iff kkt_valid
+  KktEngine *kkt = nullptr;
+  bool kkt_valid = false;
   double *ud_coef = nullptr;
   // reductions / scalars
   double *partials = nullptr; int partial_blocks = 0;
@@ -170,6 +176,16 @@ int gather_rows_public(Engine *e, const int *list, const double *scale, bool sca
 // ---- line-search building blocks (also used by the operator ABI) -----------------------------------
 int linesearch_device(Engine *e, int m, const double *Ad, const double *Ax, const double *y, const double *sigma,
                       const double *sqrt_sigma, const double *bmin, const double *bmax);  // eta/beta in scal_dev
+
+// ---- KKT factorization path (kkt.cu; newton.c:22-95, solver_interface.c:20-70,119-247) ---------------
+bool kkt_heuristic_prefers_kkt(int n, int m, const long long *Ap, const long long *Ai, const long long *Qp, const long long *Qi);
+int kkt_create(KktEngine **out, Engine *e, int n, int m, const long long *Ap, const long long *Ai, const long long *Qp, const long long *Qi);
+void kkt_destroy(KktEngine *K);
+int kkt_refactor(KktEngine *K, Engine *e, double beta);   // values for the committed active set + L S L'
+int kkt_solve(KktEngine *K, Engine *e);                   // e->d from K z = [-dphi; 0], with iterative refinement
+long long kkt_factor_nnz(const KktEngine *K);
+long long kkt_factor_count(const KktEngine *K);
+long long kkt_refine_count(const KktEngine *K);
 
 // ---- LOBPCG (nonconvex.c:29-168) ---------------------------------------------------------------------
 int lobpcg_device(Engine *e, const double *x0_host, double *lambda_out, long long *iters_out);

@@ -27,7 +27,10 @@ struct SpDev {
   int n, nsuper;
   const int *perm, *iperm, *sn_of_col, *first, *rows_off, *rowidx, *rel, *sn_parent, *child_ptr, *child_idx, *lvl_sn;
   const long long *panel_off, *upd_off;
+  const int *sgn;   // nullptr: positive definite (L L').  Otherwise the a-priori pivot signs per PERMUTED column of a
+                    // quasi-definite matrix (KKT path): the factorization is L S L', S = diag(sgn)
 };
+__device__ __forceinline__ double sgn_of(const SpDev &d, int pcol) { return d.sgn ? (double)d.sgn[pcol] : 1.0; }
 
 struct SparseChol {
   SymHost h;
@@ -69,6 +72,8 @@ static int dev_buf(SparseChol *sc, T **dst, size_t count) {
 constexpr int kSmallMaxNf = 160;   // (160 * 161 / 2 + pad) * 8 B of shared memory < 227 KB
 __host__ __device__ inline int tri_ld(int nf) { return nf | 1; }   // odd leading dimension: conflict-free column walks
 
+static int upload_symbolic(SparseChol *sc, int n);
+
 int sparse_chol_analyze(SparseChol **out, int n, int m, const int *Acsc_p, const int *Acsc_i, const int *Acsr_p,
                         const int *Acsr_j, const long long *Qp, const long long *Qi, bool force, cudaStream_t stream) {
   *out = nullptr;
@@ -88,6 +93,37 @@ int sparse_chol_analyze(SparseChol **out, int n, int m, const int *Acsc_p, const
                     "of HBM is free\n", need / 1e9, 8.0 * h.nnzL / 1e9, 8.0 * h.upd_total / 1e9, free_b / 1e9);
     delete sc; return 2;
   }
+  if (int rc = upload_symbolic(sc, n)) { sparse_chol_destroy(sc); return rc; }
+  (void)stream;
+  *out = sc;
+  return 0;
+}
+
+// Symbolic analysis of a general symmetric QUASI-DEFINITE pattern (the KKT matrix [Q + I/gamma, A_J'; A_J, -inv(Sigma_J)] of
+// src/solver_interface.c:119-170) given by its lower triangle (int64 CSC, N x N); columns >= n_pos carry negative pivots.
+// Vanderbei: every symmetric permutation of a quasi-definite matrix has an L D L' factorization whose pivot signs are those
+// of the diagonal blocks, so the signs are known before the numeric phase and no pivoting is needed.
+int sparse_ldl_analyze(SparseChol **out, int N, int n_pos, const long long *Kp, const long long *Ki, cudaStream_t stream) {
+  *out = nullptr;
+  SparseChol *sc = new SparseChol();
+  std::vector<int> zero_p((size_t)N + 1, 0), none(1, 0);
+  const int r = symbolic_analyze(N, 0, zero_p.data(), none.data(), none.data(), none.data(), Kp, Ki, true, &sc->h);
+  if (r != 0) { delete sc; return 3; }
+  size_t free_b = 0, total_b = 0;
+  QB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const double need = 8.0 * ((double)sc->h.nnzL + (double)sc->h.upd_total) + (1u << 28);
+  if (need > (double)free_b) { fprintf(stderr, "[qpalm_b200] KKT factor needs %.1f GB of HBM\n", need / 1e9); delete sc; return 2; }
+  if (int rc = upload_symbolic(sc, N)) { sparse_chol_destroy(sc); return rc; }
+  std::vector<int> sg((size_t)N);
+  for (int pj = 0; pj < N; pj++) sg[pj] = sc->h.perm[pj] >= n_pos ? -1 : 1;
+  if (int rc = up_vec(sc, &sc->d.sgn, sg)) { sparse_chol_destroy(sc); return rc; }
+  (void)stream;
+  *out = sc;
+  return 0;
+}
+
+static int upload_symbolic(SparseChol *sc, int n) {
+  SymHost &h = sc->h;
   SparseCholInfo &I = sc->info;
   I.n = n; I.nsuper = h.nsuper; I.nlevels = h.nlevels; I.max_ns = h.max_ns; I.max_nf = h.max_nf;
   I.nnzL = h.nnzL; I.upd_entries = h.upd_total; I.nnzS = h.nnzS; I.flops = h.flops;
@@ -104,10 +140,8 @@ int sparse_chol_analyze(SparseChol **out, int n, int m, const int *Acsc_p, const
   rc |= dev_buf(sc, &sc->v, (size_t)n);
   rc |= dev_buf(sc, &sc->W, (size_t)n * 8);
   rc |= dev_buf(sc, &sc->mark, (size_t)h.nsuper);
-  if (rc) { sparse_chol_destroy(sc); return rc; }
-  (void)stream;
-  *out = sc;
-  return 0;
+  d.sgn = nullptr;
+  return rc;
 }
 
 void sparse_chol_destroy(SparseChol *sc) {
@@ -232,7 +266,10 @@ __global__ void __launch_bounds__(32) k_mf_diag(SpDev d, double *panels, int lvl
   for (int j = 0; j < 32; j++) row[j] = (lane < w && j <= lane) ? B[(size_t)lane + (size_t)j * nf] : ((j == lane) ? 1.0 : 0.0);
   double dl = 1.0, dinv = 1.0;
   int badcol = -1;
-  chol32::fstep<0>(row, lane, dl, dinv, badcol);
+  if (d.sgn) {   // quasi-definite block: L S L' with the a-priori pivot signs
+    const unsigned negmask = __ballot_sync(0xffffffffu, lane < w && d.sgn[f + k0 + lane] < 0);
+    chol32::fstep_signed<0>(row, lane, dl, negmask, badcol);
+  } else chol32::fstep<0>(row, lane, dl, dinv, badcol);
 #pragma unroll
   for (int j = 0; j < 32; j++) if (lane < w && j < lane) B[(size_t)lane + (size_t)j * nf] = row[j];
   if (lane < w) B[(size_t)lane + (size_t)lane * nf] = dl;
@@ -254,6 +291,7 @@ __global__ void __launch_bounds__(128) k_mf_trsm(SpDev d, double *panels, int lv
     const int r = t & 31, c = t >> 5;
     double v = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
     if (r == c) v = 1.0 / v;          // the diagonal is stored inverted: one division per column instead of one per element
+    if (c < w) v *= sgn_of(d, f + k0 + c);   // L S L': X = A21 inv(L11') inv(S), i.e. column c of the triangle carries s_c
     Ls[r][c] = v;
   }
   __syncthreads();
@@ -286,7 +324,7 @@ __global__ void __launch_bounds__(256) k_mf_syrk(SpDev d, double *panels, double
   for (int t = threadIdx.x; t < 32 * 64; t += 256) {
     const int r = t & 63, c = t >> 6;
     As[c][r] = (c < w && i0 + r < F.nf) ? F.P[(size_t)(i0 + r) + (size_t)(k0 + c) * F.nf] : 0.0;
-    Bs[c][r] = (c < w && j0 + r < F.nf) ? F.P[(size_t)(j0 + r) + (size_t)(k0 + c) * F.nf] : 0.0;
+    Bs[c][r] = (c < w && j0 + r < F.nf) ? sgn_of(d, F.f + k0 + c) * F.P[(size_t)(j0 + r) + (size_t)(k0 + c) * F.nf] : 0.0;   // F -= P S P'
   }
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // rows tx + 16 a, cols ty + 16 b
@@ -345,15 +383,16 @@ __global__ void __launch_bounds__(256) k_mf_small(SpDev d, double *panels, doubl
   if (tid == 0) bad = 0;
   for (int k = 0; k < ns; k++) {
     __syncthreads();
-    const double dkk = Fs[k + k * ld];
+    const double sk = sgn_of(d, F.f + k);      // +1 (L L') or the a-priori pivot sign (L S L')
+    const double dkk = sk * Fs[k + k * ld];
     if (!(dkk > 0.0) && tid == 0) bad = 1 + F.f + k;
-    const double l = sqrt(dkk), linv = 1.0 / l;
+    const double l = sqrt(dkk), linv = sk / l;
     __syncthreads();
     for (int i = k + tid; i < nf; i += blockDim.x) Fs[i + k * ld] = (i == k) ? l : Fs[i + k * ld] * linv;
     __syncthreads();
     // trailing update: columns j > k, rows i >= j
     for (int j = k + 1 + warp; j < nf; j += nw) {
-      const double ljk = Fs[j + k * ld];
+      const double ljk = sk * Fs[j + k * ld];
       if (ljk == 0.0) continue;
       for (int i = j + lane; i < nf; i += 32) Fs[i + j * ld] = fma(-Fs[i + k * ld], ljk, Fs[i + j * ld]);
     }
@@ -402,6 +441,10 @@ int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *inf
 __global__ void k_sp_permute_in(SpDev d, const double *__restrict__ rhs, double *v, double sgn) {
   const int pj = blockIdx.x * blockDim.x + threadIdx.x;
   if (pj < d.n) v[pj] = sgn * rhs[d.perm[pj]];
+}
+__global__ void k_sp_apply_sign(SpDev d, double *v) {
+  const int pj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pj < d.n) v[pj] *= (double)d.sgn[pj];
 }
 __global__ void k_sp_permute_out(SpDev d, const double *__restrict__ v, double *out) {
   const int pj = blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,6 +581,7 @@ int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, con
     const int mnf = h.lvl_max_nf[l];
     QB_LAUNCH(k_mf_fwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
   }
+  if (sc->d.sgn) QB_LAUNCH(k_sp_apply_sign, cdiv(n, 256), 256, 0, st, sc->d, sc->v);   // L S L' x = b: y <- inv(S) y = S y
   for (int l = h.nlevels - 1; l >= 0; l--) {
     const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
     if (cnt <= 0) continue;

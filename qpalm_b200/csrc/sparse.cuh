@@ -35,6 +35,10 @@ struct SparseCholInfo {
 // for the sparse path to pay off (caller takes the dense path) unless `force`.
 int sparse_chol_analyze(SparseChol **out, int n, int m, const int *Acsc_p, const int *Acsc_i, const int *Acsr_p,
                         const int *Acsr_j, const long long *Qp, const long long *Qi, bool force, cudaStream_t stream);
+// The same machinery for a symmetric QUASI-DEFINITE matrix (the KKT path): pattern = lower triangle in int64 CSC, N x N,
+// columns >= n_pos have negative pivots.  Numeric phase: sparse_chol_assemble(with_Q = true, Q = the matrix as a full
+// symmetric CSR, active = nullptr, beta = 0) + sparse_chol_factor (L S L') + sparse_chol_solve.
+int sparse_ldl_analyze(SparseChol **out, int N, int n_pos, const long long *Kp, const long long *Ki, cudaStream_t stream);
 void sparse_chol_destroy(SparseChol *sc);
 const SparseCholInfo *sparse_chol_info(const SparseChol *sc);
 size_t sparse_chol_factor_doubles(const SparseChol *sc);   // doubles of one numeric factor (panels)

@@ -242,6 +242,31 @@ def grid_qp(g, seed=0, box=1.0, diag_shift=0.0, name=None, **settings) -> QP:
     return QP(name or f"grid_qp_g{g}", CSC(n, n, Ql.indptr, Ql.indices, Ql.data, -1), CSC.from_scipy(A), q, bmin, bmax, 0.0, st)
 
 
+def kkt_standin_qp(n=2500, seed=0, dense_rows=3, name=None, **settings) -> QP:
+    """AUG2DCQP-class stand-in (SYNTHETIC: the Maros-Meszaros files are absent): a sparse QP whose Schur complement
+    Q + A'A FILLS IN.  Q = SPD tridiagonal, A = [banded difference rows (n - 1); `dense_rows` coupling rows that touch every
+    variable (budget-type constraints); identity box rows (n)].  One active coupling row makes A_J' Sigma A_J completely dense,
+    while the KKT matrix [Q + I/gamma, A_J'; A_J, -inv(Sigma_J)] keeps nnz(A) + nnz(Q) entries -- the case
+    qpalm_set_factorization_method (src/solver_interface.c:20-66) sends to FACTORIZE_KKT."""
+    rng = np.random.default_rng(seed)
+    main = 2.0 + rng.random(n)
+    off = -0.5 * rng.random(n - 1)
+    Ql = sp.diags([main, off], [0, -1], format="csc")
+    Ql.sort_indices()
+    rows = [sp.diags([np.ones(n - 1), -np.ones(n - 1)], [0, 1], shape=(n - 1, n), format="csr")]
+    rows.append(sp.csr_matrix(0.5 + rng.random((dense_rows, n))))
+    rows.append(sp.eye(n, format="csr"))
+    A = sp.vstack(rows).tocsc()
+    A.sort_indices()
+    m = A.shape[0]
+    q = rng.standard_normal(n)
+    bmin = np.concatenate([-0.3 * np.ones(n - 1), -np.ones(dense_rows), -0.5 - rng.random(n)])
+    bmax = np.concatenate([0.3 * np.ones(n - 1), np.ones(dense_rows), 0.5 + rng.random(n)])
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, verbose=0)
+    st.update(settings)
+    return QP(name or f"kkt_standin_n{n}", CSC(n, n, Ql.indptr, Ql.indices, Ql.data, -1), CSC.from_scipy(A), q, bmin, bmax, 0.0, st)
+
+
 def _gram(M: np.ndarray) -> np.ndarray:
     """M M' in fp64; uses the GPU through torch when one is visible (data generation only)."""
     try:
