@@ -818,7 +818,7 @@ __device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *
         if (lane < k) { cf.wj[j][lane] = wj; cf.gam[j][lane] = gam; }
         __syncwarp();
         {
-          double t = Pn[j * LDP + (lane & (UW - 1))] * winv;
+          double t = ((lane < w) ? Pn[j * LDP + lane] : 0.0) * winv;   // predicated load: lanes beyond the block read nothing
 #pragma unroll
           for (int r = 0; r < KU; r++) {
             wl[r] = fma(-cf.wj[j][r], t, wl[r]);

@@ -142,6 +142,140 @@ k_dgemm_nt(int K, const double *A, int lda, const double *B, int ldb,
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same GEMM with the tile movement on the TMA engine: bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) issued by a
+// PRODUCER warp and completed on mbarriers, instead of 16 cp.async (LDGSTS) instructions per thread and stage.
+//   * warps 0-7 only compute (no address arithmetic, no copy instructions, no __syncthreads in the main loop);
+//   * warp 8 owns the pipeline: per k-tile it waits for the stage's `empty` barrier (one arrival per consumer warp), posts
+//     the expected byte count on the `full` barrier and issues ONE bulk copy per lane: lanes 0-15 the 16 k-columns of the A
+//     tile, lanes 16-31 those of the B tile (each a contiguous run of BM_ / BN doubles of the column-major operand, landing
+//     in the padded k-major row the fragment loads expect);
+//   * 4 stages instead of 3 (the registers the consumers no longer spend on copies pay for nothing else, shared memory does).
+// Every operand column start is 16-byte aligned (leading dimensions are multiples of 128, tile origins multiples of 64).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TSTAGES = 4;
+template <int BM_> constexpr size_t smem_bytes_tma() { return sizeof(double) * TSTAGES * BK * ((BM_ + 4) + (BN + 4)) + 2 * TSTAGES * sizeof(unsigned long long); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int BM_>
+__global__ void __launch_bounds__(288, 1)
+k_dgemm_nt_tma(int K, const double *A, int lda, const double *B, int ldb,
+               double *C, int ldc, double alpha, double beta, int lower_only,
+               long long sA, long long sB, long long sC, const int *Kz, const int *maskz) {
+  constexpr int SROWA = BM_ + 4, SROWB = BN + 4;
+  constexpr int WM = BM_ / 64, WN = 8 / WM, NF = BN / (8 * WN);
+  const int bm = blockIdx.x, bn = blockIdx.y;
+  if (lower_only && bn * BN >= (bm + 1) * BM_) return;
+  if (maskz && !maskz[blockIdx.z]) return;
+  if (Kz) K = Kz[blockIdx.z];
+  if (K <= 0 && beta == 1.0) return;
+  A += (size_t)blockIdx.z * sA; B += (size_t)blockIdx.z * sB; C += (size_t)blockIdx.z * sC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef double TileA[BK][SROWA];
+  typedef double TileB[BK][SROWB];
+  TileA *As = reinterpret_cast<TileA *>(smem_raw);
+  TileB *Bs = reinterpret_cast<TileB *>(smem_raw + sizeof(double) * TSTAGES * BK * SROWA);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(double) * TSTAGES * BK * (SROWA + SROWB));
+  unsigned long long *empty = full + TSTAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KT = K / BK;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TSTAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 8) {   // ---- producer ----
+    const double *Ag = A + (size_t)bm * BM_, *Bg = B + (size_t)bn * BN;
+    constexpr unsigned kBytes = sizeof(double) * BK * (BM_ + BN);
+    for (int kt = 0; kt < KT; kt++) {
+      const int st = kt % TSTAGES;
+      if (kt >= TSTAGES) mbar_wait(empty + st, ((kt / TSTAGES) - 1) & 1);   // the consumers have drained this stage
+      if (lane == 0) mbar_expect_tx(full + st, kBytes);
+      __syncwarp();
+      const int kk = lane & 15;
+      if (lane < 16) bulk_g2s(&As[st][kk][0], Ag + (size_t)(kt * BK + kk) * lda, sizeof(double) * BM_, full + st);
+      else bulk_g2s(&Bs[st][kk][0], Bg + (size_t)(kt * BK + kk) * ldb, sizeof(double) * BN, full + st);
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int wm = warp % WM, wn = warp / WM;
+  double acc[8][NF][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < NF; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int kt = 0; kt < KT; kt++) {
+    const int st = kt % TSTAGES;
+    mbar_wait(full + st, (kt / TSTAGES) & 1);
+    double a[2][8], b[2][NF];
+#pragma unroll
+    for (int mb = 0; mb < 8; mb++) a[0][mb] = As[st][fk][wm * 64 + mb * 8 + fr];
+#pragma unroll
+    for (int nb = 0; nb < NF; nb++) b[0][nb] = Bs[st][fk][wn * (8 * NF) + nb * 8 + fr];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int cur = ks & 1, nxt = cur ^ 1;
+      if (ks < 3) {
+#pragma unroll
+        for (int mb = 0; mb < 8; mb++) a[nxt][mb] = As[st][(ks + 1) * 4 + fk][wm * 64 + mb * 8 + fr];
+#pragma unroll
+        for (int nb = 0; nb < NF; nb++) b[nxt][nb] = Bs[st][(ks + 1) * 4 + fk][wn * (8 * NF) + nb * 8 + fr];
+      }
+#pragma unroll
+      for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+        for (int nb = 0; nb < NF; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[cur][mb], b[cur][nb]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);   // this warp is done with the stage
+  }
+  // every bulk copy of this CTA has been waited for: C may alias A from here on
+  const bool use_beta = (beta != 0.0);
+#pragma unroll
+  for (int mb = 0; mb < 8; mb++) {
+    const int row = bm * BM_ + wm * 64 + mb * 8 + fr;
+#pragma unroll
+    for (int nb = 0; nb < NF; nb++) {
+      const int col = bn * BN + wn * (8 * NF) + nb * 8 + 2 * fk;
+      double *c0 = C + row + (size_t)col * ldc;
+      double *c1 = c0 + ldc;
+      double v0 = alpha * acc[mb][nb][0], v1 = alpha * acc[mb][nb][1];
+      if (use_beta) { v0 += beta * (*c0); v1 += beta * (*c1); }
+      *c0 = v0; *c1 = v1;
+    }
+  }
+}
 }  // namespace gemm
 
 static int gemm_attr() {
@@ -149,6 +283,8 @@ static int gemm_attr() {
   if (!attr_set) {
     QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes<128>()));
     QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes<64>()));
+    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes_tma<128>()));
+    QB_CUDA_TRY(cudaFuncSetAttribute(gemm::k_dgemm_nt_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::smem_bytes_tma<64>()));
     attr_set = true;
   }
   return 0;
@@ -168,14 +304,21 @@ int dgemm_nt_batched(cudaStream_t s, int nb, int M, int N, int K, const int *Kz,
   const long long tiles = (lower_only ? (nt <= mt ? nt * mt - nt * (nt - 1) / 2 : mt * (mt + 1) / 2) : mt * nt) * nb;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; QB_CUDA_TRY(cudaGetDevice(&dev)); QB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  // tile movement on the TMA engine (bulk async copies + mbarriers, producer warp) unless QPALM_B200_GEMM_LDGSTS=1 (A/B runs);
+  // the in-place panel solve (C aliases A across CTAs of one tile column is CTA-local, see the kernel) takes either path
+  static const bool legacy = getenv("QPALM_B200_GEMM_LDGSTS") != nullptr;
   if (tiles < num_sms) {
     dim3 grid(M / 64, N / gemm::BN, nb);
-    QB_LAUNCH(gemm::k_dgemm_nt<64>, grid, 256, gemm::smem_bytes<64>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
-              lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+    if (legacy) QB_LAUNCH(gemm::k_dgemm_nt<64>, grid, 256, gemm::smem_bytes<64>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+                          lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+    else QB_LAUNCH(gemm::k_dgemm_nt_tma<64>, grid, 288, gemm::smem_bytes_tma<64>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+                   lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
   } else {
     dim3 grid(M / gemm::BM, N / gemm::BN, nb);
-    QB_LAUNCH(gemm::k_dgemm_nt<128>, grid, 256, gemm::smem_bytes<128>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
-              lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+    if (legacy) QB_LAUNCH(gemm::k_dgemm_nt<128>, grid, 256, gemm::smem_bytes<128>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+                          lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
+    else QB_LAUNCH(gemm::k_dgemm_nt_tma<128>, grid, 288, gemm::smem_bytes_tma<128>(), s, K, A, lda, B, ldb, C, ldc, alpha, beta,
+                   lower_only ? 1 : 0, sA, sB, sC, Kz, maskz);
   }
   QB_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -1762,7 +1762,8 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
     const bool sparse_data = !e->A_dense && !e->Q_dense && m > 0 && e->sh_world == 1;
     bool want_kkt = sparse_data && (newton_override == 3 || (!newton_override && newton_mode && !strcmp(newton_mode, "kkt")));
     // (measured: below n ~ 6000 the dense DMMA factor of the filled-in Schur complement is still faster than the level-scheduled KKT factor)
-    static const int kkt_auto_min_n = [] { const char *s = getenv("QPALM_B200_KKT_AUTO_MIN_N"); return s ? atoi(s) : 6000; }();
+    const char *kkt_min_s = getenv("QPALM_B200_KKT_AUTO_MIN_N");
+    const int kkt_auto_min_n = kkt_min_s ? atoi(kkt_min_s) : 6000;
     if (!want_kkt && sparse_data && !newton_override && !newton_mode && !e->sp && n >= kkt_auto_min_n)
       want_kkt = kkt_heuristic_prefers_kkt(n, m, Ap, Ai, Qp, Qi);
     if (want_kkt) {

@@ -242,6 +242,72 @@ def grid_qp(g, seed=0, box=1.0, diag_shift=0.0, name=None, **settings) -> QP:
     return QP(name or f"grid_qp_g{g}", CSC(n, n, Ql.indptr, Ql.indices, Ql.data, -1), CSC.from_scipy(A), q, bmin, bmax, 0.0, st)
 
 
+def probe_qp(n=1000, m=2000, dens_A=0.05, dens_M=0.007, nonconvex=False, **settings) -> QP:
+    """The survey's probe instance, bit for bit: xorshift64 (s ^= s << 13; s ^= s >> 7; s ^= s << 17, start
+    88172645463325252), uniform u = (s >> 11) / 2^53, normal = sqrt(-2 ln(u1 + 1e-300)) cos(2 pi u2); A drawn column-major (one
+    uniform per entry, a normal when it is < dens_A), then M the same way, Q = M M' accumulated in k-outer order (optionally
+    Q_ii -= 1), stored lower with exact-zero off-diagonals dropped and the diagonal always kept, then q (n normals), then per row
+    bmin = -u, bmax = u.  With the defaults: nnz(A) = 99 803, nnz(Q lower) = 25 154 and the reference returns solved, 52 / 4
+    iterations, objective -4.0571425653e+01 (appendix D) -- an oracle cross-check that does not depend on numpy's generators."""
+    import math
+    mask = (1 << 64) - 1
+    state = [88172645463325252]
+
+    def uni():
+        s = state[0]
+        s ^= (s << 13) & mask
+        s ^= s >> 7
+        s ^= (s << 17) & mask
+        state[0] = s
+        return (s >> 11) / 9007199254740992.0
+
+    def normal():
+        u1 = uni()
+        u2 = uni()
+        return math.sqrt(-2.0 * math.log(u1 + 1e-300)) * math.cos(2.0 * math.pi * u2)
+
+    def draw(nrow, ncol, dens):
+        p, idx, val = [0], [], []
+        for _ in range(ncol):
+            for i in range(nrow):
+                if uni() < dens:
+                    idx.append(i)
+                    val.append(normal())
+            p.append(len(idx))
+        return p, idx, val
+
+    Ap, Ai, Ax = draw(m, n, dens_A)
+    Mp, Mi, Mx = draw(n, n, dens_M)
+    Qd = np.zeros((n, n))
+    for k in range(n):                                   # k-outer accumulation: Q += M[:, k] M[:, k]'
+        rows = Mi[Mp[k]:Mp[k + 1]]
+        vals = Mx[Mp[k]:Mp[k + 1]]
+        for a, va in zip(rows, vals):
+            for b, vb in zip(rows, vals):
+                Qd[a, b] += va * vb
+    if nonconvex:
+        Qd[np.diag_indices(n)] -= 1.0
+    Qp, Qi, Qx = [0], [], []
+    for j in range(n):
+        col = Qd[j:, j]
+        keep = np.nonzero(col)[0]
+        if keep.size == 0 or keep[0] != 0:
+            keep = np.concatenate([[0], keep])           # the diagonal is always stored
+        Qi.extend((keep + j).tolist())
+        Qx.extend(col[keep].tolist())
+        Qp.append(len(Qi))
+    q = np.array([normal() for _ in range(n)])
+    bmin, bmax = np.empty(m), np.empty(m)
+    for i in range(m):
+        bmin[i] = -uni()
+        bmax[i] = uni()
+    st = dict(eps_abs=1e-6, eps_rel=1e-6, verbose=0)
+    if nonconvex:
+        st["nonconvex"] = 1
+    st.update(settings)
+    return QP(f"probe_qp_n{n}_m{m}", _csc(n, n, Qp, Qi, Qx, -1), _csc(m, n, Ap, Ai, Ax), q, bmin, bmax, 0.0, st)
+
+
 def kkt_standin_qp(n=2500, seed=0, dense_rows=3, name=None, **settings) -> QP:
     """AUG2DCQP-class stand-in (SYNTHETIC: the Maros-Meszaros files are absent): a sparse QP whose Schur complement
     Q + A'A FILLS IN.  Q = SPD tridiagonal, A = [banded difference rows (n - 1); `dense_rows` coupling rows that touch every

@@ -219,3 +219,10 @@ def test_mpc_instance():
     """One chain80w-sized instance (n=240, m=949, dense), BASELINE config 4 settings."""
     b = problems.mpc_batch(2, seed=1)
     _check(b.instance(0))
+
+
+def test_appendix_e_probe_instance_on_the_gpu():
+    """the xorshift64 probe instance (BASELINE config 1 shape): solved, 52 / 4, objective -4.0571425653e+01."""
+    p = problems.probe_qp()
+    g = _check(p)
+    assert (g.iter, g.iter_out) == (52, 4) and abs(g.objective + 4.0571425653e+01) < 1e-8 * 40.6

@@ -187,3 +187,16 @@ def test_linesearch_oracle_vs_bruteforce(oracle_ops):
         assert np.all(np.diff(s) >= 0)
         ties = np.diff(s) == 0
         assert np.all(np.diff(idx)[ties] > 0)
+
+
+def test_appendix_e_probe_instance():
+    """the xorshift64 + Box-Muller probe instance has nnz(A) = 99 803, nnz(Q lower) = 25 154 and the
+    reference returns solved, 52 / 4 iterations, objective -4.0571425653e+01 -- reproduced here by the oracle (and by the
+    compiled reference when it is present), independently of numpy's generators."""
+    p = problems.probe_qp()
+    assert int(p.A.p[-1]) == 99803 and int(p.Q.p[-1]) == 25154
+    impls = ["oracle"] + (["reference"] if HAS_REF else [])
+    for impl in impls:
+        r = solve_qp(impl, p.Q.copy(), p.A.copy(), p.q.copy(), p.bmin.copy(), p.bmax.copy(), **p.settings)
+        assert r.status_val == 1 and (r.iter, r.iter_out) == (52, 4), (impl, r.iter, r.iter_out)
+        assert abs(r.objective - (-4.0571425653e+01)) < 1e-8 * 40.6, (impl, r.objective)
