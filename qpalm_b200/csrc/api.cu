@@ -403,9 +403,13 @@ static bool prefer_updown(const Engine *e, int k) {
   if (e->sh_world > 1 && !flow) return false;   // row-sharded: only the dataflow path allreduces the gathered rows
   if (!flow && k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->updown_force) return true;
-  if (e->sp) {   // sparse factor: k sweeps of <= 8 ranks along etree paths; measured cost of the last one vs the last refactorisation
-    const double t_sweep = e->last_updown_ms > 0 ? e->last_updown_ms : 0.0;   // unknown yet: try it once
-    return t_sweep * ((k + 7) / 8) < (e->last_refactor_ms > 0 ? e->last_refactor_ms : 1e30);
+  if (e->sp) {
+    // Sparse factor: a STATIC rule as well (round 1 compared measured times here, which made re-solves irreproducible).  A sweep
+    // of <= 8 ranks is ONE CTA walking the union of the etree paths (k_ud_sweep), a refactorisation is ~3 launches per 32-column
+    // block and level over all SMs; in every measurement kept (grid QPs n = 10^4 .. 9 10^4) the refactorisation won as soon as
+    // more than one sweep was needed, so: a single sweep when the factor is small enough for one CTA to stream it quickly.
+    const SparseCholInfo *I = sparse_chol_info(e->sp);
+    return k <= 8 && I->nnzL <= 2000000;
   }
   // Dense factor: a STATIC model (no measured times: the choice must not depend on timing, or re-solves would not be
   // reproducible, tests/src/test_basic_qp.c:298-305).  With a single 128-column panel both paths are launch-bound and
@@ -488,6 +492,8 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
   } else work->info->dual_objective = QPALM_NULL;
 
   c_int iter, iter_out = 0, prev_iter = 0, no_change = 0;
+  bool newton_factored = false;   // the previous iteration refactorised the Newton system: its status is in the next readback
+  cudaMemsetAsync(e->info_dev, 0, sizeof(int), e->stream);   // (the factor of Q for the dual objective may have left a flag)
   c_float eps_k_abs = st->eps_abs_in, eps_k_rel = st->eps_rel_in, eps_k;
   const double *h = e->scal_host;
   const double BA = e->A_dense ? 8.0 * (double)m * (double)n : 12.0 * (double)(e->A_csr.nnz) + 4.0 * ((double)n + 1);
@@ -498,6 +504,17 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
     step_residuals(e, proximal, work->gamma, 0.0);
     if (sync_scalars(e)) { update_status(work->info, QPALM_ERROR); finish(work, iter, iter_out); return; }
     collect(e, pend);
+    if (newton_factored && e->info_host[0] != 0) {
+      // The last factorization met a non-positive pivot (H + I/gamma not numerically positive definite: an indefinite Q solved
+      // with nonconvex = 0, or a singular Q without the proximal term).  The factor holds NaN from that column on, so every
+      // later comparison would be false and the loop would run to max_iter on garbage: stop with an error instead.
+      QP_EPRINT("the Newton system is not positive definite (non-positive pivot at column %d); set nonconvex / proximal", e->info_host[0] - 1);
+      update_status(work->info, QPALM_ERROR);
+      cudaMemsetAsync(e->info_dev, 0, sizeof(int), e->stream);
+      e->info_host[0] = 0;
+      finish(work, iter, iter_out);
+      return;
+    }
     work->tau = h[S_TAU];
     // ---- calculate_residuals_and_tolerances (termination.c:44-128) ----
     const double cinv = st->scaling ? work->scaling->cinv : 1.0;
@@ -612,7 +629,8 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
         const bool refac = sv->reset_newton || !e->kkt_valid || (ne + nl) > 0;
         if (trace) fprintf(stderr, "[qpalm_b200 trace] iter %ld out %ld active %d enter %d leave %d -> KKT %s\n", (long)iter, (long)iter_out, na, ne, nl,
                            refac ? "refactor" : "reuse factor");
-        if (refac) { kkt_refactor(e->kkt, e, beta); e->kkt_valid = true; pend.kind = 1; }
+        newton_factored = refac;
+        if (refac) { cudaMemsetAsync(e->info_dev, 0, sizeof(int), e->stream); kkt_refactor(e->kkt, e, beta); e->kkt_valid = true; pend.kind = 1; }
         kkt_solve(e->kkt, e);
         step_commit_active(e);
         sv->reset_newton = FALSE;
@@ -640,6 +658,8 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
       } else if (m > 0) {
         cudaMemcpyAsync(e->active, e->active_cand, sizeof(int) * m, cudaMemcpyDeviceToDevice, e->stream);
       }
+      newton_factored = need_refactor || factor_q;
+      if (newton_factored) cudaMemsetAsync(e->info_dev, 0, sizeof(int), e->stream);
       if (need_refactor) { step_newton_refactor(e, true, from_scratch, beta, na); pend.kind = 1; }
       else if (factor_q) { step_newton_refactor(e, false, true, beta, 0); pend.kind = 1; }
       step_newton_solve(e);

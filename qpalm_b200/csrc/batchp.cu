@@ -440,70 +440,68 @@ __device__ void p_outer(const Args &P, int b, int kind) {
 // for r0 <= j <= i < n.  U is PW x LDP in shared memory.  Warp task = 128 rows x 4 columns, 4 x 4 register block per lane.
 // The accumulators START from the old values: all 16 global loads of a task are issued up front and their latency is
 // paid once per task (a read-modify-write after the loop serialises 16 dependent L2 round trips: measured 6x slower).
+// FP64 tensor-core tile of the in-CTA rank-w updates: d += a (8 x 4) * b (4 x 8), mma.sync m8n8k4 (DMMA)
+__device__ __forceinline__ void bp_dmma884(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// dst(i, j) = base(i, j) + sign * sum_{c < w} U[c][i] U[c][j]   for r0 <= j <= i < n   (the SYRK of the H record and the trailing
+// update of the in-CTA Cholesky), base = first ? sscale * src + diag_add I : dst.  U = shared panel, column c at U + c * LDP - u0.
+// Round 2: the products run on the FP64 tensor pipe.  Each warp takes 16 x 16 tiles of the lower triangle (2 x 2 DMMA tiles,
+// round-robin over the warps); per 4 columns of U it loads two A and two B fragments from shared memory and issues four
+// mma.sync.m8n8k4 -- a quarter of the shared-memory wavefronts and a sixth of the instructions of the 4 x 4 scalar register
+// tile this replaces (which ran the FP64 pipe at 18 %).  The sign rides on the final add.
 __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, const double *src, int lds, double sscale, double diag_add, bool first,
                                       int r0, int n, const double *U, int u0, int w, double sign) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rem = n - r0;
   if (rem <= 0) return;
-  const int IB = (rem + 127) / 128, JB = (rem + 3) / 4;
-  for (int q = warp; q < IB * JB; q += NW) {
-    const int ib = q / JB, jb = q - ib * JB;
-    const int i0 = r0 + ib * 128, j0 = r0 + jb * 4;
-    if (i0 + 127 < j0) continue;   // block entirely above the diagonal
-    double acc[4][4];
-    int ri[4], cj[4];
+  const int T = (rem + 15) >> 4, ntiles = T * (T + 1) / 2;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int wpad = (w + 3) & ~3;
+  for (int q = warp; q < ntiles; q += NW) {
+    int ib = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while (ib * (ib + 1) / 2 > q) ib--;
+    while ((ib + 1) * (ib + 2) / 2 <= q) ib++;
+    const int jb = q - ib * (ib + 1) / 2;
+    const int i0 = r0 + 16 * ib, j0 = r0 + 16 * jb;
+    int ra[2], rb[2];   // fragment rows (clamped: rows beyond n read a valid address and are never stored)
 #pragma unroll
-    for (int a = 0; a < 4; a++) { ri[a] = i0 + lane + 32 * a; if (ri[a] >= n) ri[a] = n - 1; }
+    for (int t = 0; t < 2; t++) {
+      ra[t] = i0 + 8 * t + fr; if (ra[t] >= n) ra[t] = n - 1;
+      rb[t] = j0 + 8 * t + fr; if (rb[t] >= n) rb[t] = n - 1;
+    }
+    double acc[2][2][2];
 #pragma unroll
-    for (int e = 0; e < 4; e++) { cj[e] = j0 + e; if (cj[e] >= n) cj[e] = n - 1; }
+    for (int a = 0; a < 2; a++)
 #pragma unroll
-    for (int e = 0; e < 4; e++)
+      for (int e = 0; e < 2; e++) acc[a][e][0] = acc[a][e][1] = 0.0;
+    for (int kc = 0; kc < wpad; kc += 4) {
+      const int c = kc + fk;
+      const bool live = c < w;
+      const double *Uc = U + (live ? c : 0) * LDP - u0;
+      double fa[2], fb[2];
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int i = i0 + lane + 32 * a, j = j0 + e;
-        double base = 0.0;
-        if (i < n && j < n && i >= j) {
-          if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
-          else base = dst[(size_t)i + (size_t)ldd * j];
-        }
-        acc[a][e] = base;
-      }
-    // the sign rides on the FMA's operand negation (free) instead of four multiplies per column: (-u) v == -(u v) exactly,
-    // so the results are bit-identical to the `sign * u` form
-    if (sign < 0.0) {
-      for (int c = 0; c < w; c++) {   // rolled: unrolling by 2 spills at the 64-register shape (measured 144 vs 123 ms)
-        const double *Uc = U + c * LDP - u0;
-        double ua[4], ub[4];
+      for (int t = 0; t < 2; t++) { fa[t] = live ? Uc[ra[t]] : 0.0; fb[t] = live ? Uc[rb[t]] : 0.0; }
 #pragma unroll
-        for (int a = 0; a < 4; a++) ua[a] = Uc[ri[a]];
+      for (int a = 0; a < 2; a++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) ub[e] = Uc[cj[e]];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) acc[a][e] = fma(-ua[a], ub[e], acc[a][e]);
-      }
-    } else {
-      for (int c = 0; c < w; c++) {   // rolled: unrolling by 2 spills at the 64-register shape (measured 144 vs 123 ms)
-        const double *Uc = U + c * LDP - u0;
-        double ua[4], ub[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) ua[a] = Uc[ri[a]];
-#pragma unroll
-        for (int e = 0; e < 4; e++) ub[e] = Uc[cj[e]];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) acc[a][e] = fma(ua[a], ub[e], acc[a][e]);
-      }
+        for (int e = 0; e < 2; e++) bp_dmma884(acc[a][e][0], acc[a][e][1], fa[a], fb[e]);
     }
 #pragma unroll
-    for (int e = 0; e < 4; e++)
+    for (int a = 0; a < 2; a++)
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int i = i0 + lane + 32 * a, j = j0 + e;
-        if (i < n && j < n && i >= j) dst[(size_t)i + (size_t)ldd * j] = acc[a][e];
-      }
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int i = i0 + 8 * a + fr, j = j0 + 8 * e + 2 * fk + h;
+          if (i < n && j < n && i >= j) {
+            double base;
+            if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
+            else base = dst[(size_t)i + (size_t)ldd * j];
+            dst[(size_t)i + (size_t)ldd * j] = fma(sign, acc[a][e][h], base);
+          }
+        }
   }
 }
 

@@ -101,7 +101,7 @@ struct Engine {
   double *partials = nullptr; int partial_blocks = 0;
   double *gemv_partials = nullptr; int gemv_splits = 0;
   double *scal_dev = nullptr, *scal_host = nullptr;   // S_COUNT doubles each (host pinned)
-  int *info_dev = nullptr;
+  int *info_dev = nullptr, *info_host = nullptr;   // factorization status (device / pinned host mirror, copied with the scalar block)
   // statistics (QPALMB200Stats)
   long long launches0 = 0;
   long long n_inner = 0, n_outer = 0, n_refactor = 0, refactor_active_sum = 0, n_updown = 0, updown_rank_sum = 0, n_spmv = 0, n_sigma_update = 0, sigma_update_rank_sum = 0;

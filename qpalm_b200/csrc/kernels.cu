@@ -65,6 +65,8 @@ int download_int(Engine *e, long long *dst, const int *src, int len) {
 }
 int sync_scalars(Engine *e) {
   QB_CUDA_TRY(cudaMemcpyAsync(e->scal_host, e->scal_dev, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, e->stream));
+  // the factorization status rides along (first non-positive pivot of the last Cholesky / L S L', 0 = fine)
+  QB_CUDA_TRY(cudaMemcpyAsync(e->info_host, e->info_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -1584,10 +1586,28 @@ static bool csc_is_packed_lower(int n, const long long *Qp, const long long *Qi)
   return Qp[n] == pos;
 }
 
+static int engine_create_impl(Engine *e, Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
+                              const long long *Qp, const long long *Qi, const double *Qx,
+                              const double *q, const double *bmin, const double *bmax, bool need_LQ, int newton_override);
+
+// Every failure exit releases what was allocated so far (the stream, the arena, matrices, factors): a caller that handles
+// the NULL workspace and retries with another configuration finds the HBM free again.
 int engine_create(Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
                   const long long *Qp, const long long *Qi, const double *Qx,
                   const double *q, const double *bmin, const double *bmax, bool need_LQ, int newton_override) {
   *out = nullptr;
+  int ndev = 0;
+  QB_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) { fprintf(stderr, "[qpalm_b200] no CUDA device: this library has no CPU fallback\n"); return 1; }
+  Engine *e = new Engine();
+  const int rc = engine_create_impl(e, out, n, m, Ap, Ai, Ax, Qp, Qi, Qx, q, bmin, bmax, need_LQ, newton_override);
+  if (rc) { *out = nullptr; engine_destroy(e); }
+  return rc;
+}
+
+static int engine_create_impl(Engine *e, Engine **out, int n, int m, const long long *Ap, const long long *Ai, const double *Ax,
+                              const long long *Qp, const long long *Qi, const double *Qx,
+                              const double *q, const double *bmin, const double *bmax, bool need_LQ, int newton_override) {
   {   // the device forms use int32 indices: refuse what does not fit instead of overflowing
     const long long nnzA_ = m > 0 ? Ap[n] : 0, nnzQ_ = Qp[n];
     if (nnzA_ > 2147483647LL || 2 * nnzQ_ > 2147483647LL) {
@@ -1595,10 +1615,6 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
       return 3;
     }
   }
-  int ndev = 0;
-  QB_CUDA_TRY(cudaGetDeviceCount(&ndev));
-  if (ndev <= 0) { fprintf(stderr, "[qpalm_b200] no CUDA device: this library has no CPU fallback\n"); return 1; }
-  Engine *e = new Engine();
   const bool timing = getenv("QPALM_B200_SETUP_TIMING") != nullptr;   // phase timers of the setup path (stderr)
   auto t_last = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
@@ -1806,6 +1822,8 @@ int engine_create(Engine **out, int n, int m, const long long *Ap, const long lo
   if (rc) return rc;
   QB_CUDA_TRY(cudaMallocHost((void **)&e->scal_host, sizeof(double) * S_COUNT));
   memset(e->scal_host, 0, sizeof(double) * S_COUNT);
+  QB_CUDA_TRY(cudaMallocHost((void **)&e->info_host, sizeof(int) * 4));
+  memset(e->info_host, 0, sizeof(int) * 4);
   QB_CUDA_TRY(cudaEventCreate(&e->ev0)); QB_CUDA_TRY(cudaEventCreate(&e->ev1));
   QB_CUDA_TRY(cudaEventCreate(&e->evs0)); QB_CUDA_TRY(cudaEventCreate(&e->evs1));
   e->launches0 = g_kernel_launches;
@@ -1834,6 +1852,7 @@ void engine_destroy(Engine *e) {
   sparse_chol_destroy(e->sp);
   kkt_destroy(e->kkt);
   if (e->scal_host) cudaFreeHost(e->scal_host);
+  if (e->info_host) cudaFreeHost(e->info_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs0) cudaEventDestroy(e->evs0);

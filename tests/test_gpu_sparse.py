@@ -143,7 +143,14 @@ def test_known_answer_qps_through_the_sparse_factor(make, kw):
     p = make()
     g, stats = _solve_with_stats(p, env={"QPALM_B200_NEWTON": "sparse"}, **kw)
     assert stats.sparse_factor_nnz > 0
-    _gates(g, _ref(p, **kw))
+    r = _ref(p, **kw)
+    if p.name == "dua_inf":
+        # tests/src/test_dua_inf_qp.c pins the STATUS only: with Q = 1e-10 I the iteration at which the certificate fires depends on
+        # the last bits of the factor (round 1 matched 7 iterations only through a timing-dependent refactor-vs-update choice; the
+        # choice is a static rule now and this 2-variable problem forced through the supernodal path fires at iteration 5)
+        assert g.status_val == r.status_val == -4
+    else:
+        _gates(g, r)
     if p.expect_x is not None and g.status_val == 1:
         np.testing.assert_allclose(g.x, p.expect_x, rtol=1e-5, atol=1e-5)
 
@@ -193,3 +200,24 @@ def test_nonconvex_through_the_sparse_factor(shift):
     r = _ref(p)
     assert stats.sparse_factor_nnz > 0
     _gates(g, r, tol=1e-5, iter_tol=0.1)
+
+
+def test_sparse_resolve_is_bit_reproducible():
+    """tests/src/test_basic_qp.c:298-305 on the supernodal sparse path: a second solve from the same start reproduces x, y exactly
+    (the refactor-vs-update choice is a static rule, not a timing comparison)."""
+    p = problems.grid_qp(26, seed=4)
+    s = Qpalm("b200")
+    for k, v in p.settings.items():
+        setattr(s.settings, k, v)
+    s.set_data(p.Q, p.A, p.q, p.bmin, p.bmax)
+    assert s._allocate_work()
+    x0, y0 = s.vec("x", p.n), s.vec("y", p.m)
+    outs = []
+    for _ in range(3):
+        s._warm_start(x0, y0)
+        s._solve()
+        outs.append(s.result())
+    s.cleanup()
+    for r in outs[1:]:
+        assert r.iter == outs[0].iter and r.iter_out == outs[0].iter_out
+        assert np.array_equal(r.x, outs[0].x) and np.array_equal(r.y, outs[0].y)
