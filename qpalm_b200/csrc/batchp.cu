@@ -114,6 +114,40 @@ struct Smem {
 // ------------------------------------------------------------------------------------------------
 #define RED_OUT(op, val, slot) { const double r_ = block_red<op>(val, scratch); if (threadIdx.x == 0) BSC(b, slot) = r_; }
 
+// K block reductions behind ONE pair of barriers (block_red pays two barriers per value: p_res_m alone had 22).  Stage 1 is
+// block_red's warp butterfly; stage 2 replays, in one thread per value, the tree that block_red's second butterfly forms over
+// the per-warp partials (lanes >= NW hold the identity there), so every result is bit-identical to block_red's.
+constexpr int RED_MULTI_MAX = 12;
+__device__ __forceinline__ double red_dyn(int op, double a, double b) { return op == RED_SUM ? a + b : (op == RED_MAX ? fmax(a, b) : fmin(a, b)); }
+template <int K>
+__device__ __forceinline__ void block_red_multi(const Args &P, int b, const double (&val)[K], const int (&op)[K], const int (&slot)[K], double *part_buf) {
+  static_assert(K <= RED_MULTI_MAX && NW <= 8 && RED_MULTI_MAX * 8 <= VS_LEN, "partials live in the staged-vector buffer (free between phases)");
+  double (*part)[8] = reinterpret_cast<double (*)[8]>(part_buf);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();   // the previous user of part[] is done
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double x = val[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = red_dyn(op[k], x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (lane == 0) part[k][wid] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (threadIdx.x == (k % NW) * 32 + k / NW) {
+      double a[8];
+#pragma unroll
+      for (int w = 0; w < 8; w++) a[w] = (w < NW) ? part[k][w] : (op[k] == RED_SUM ? 0.0 : (op[k] == RED_MAX ? -1.0e300 : 1.0e300));
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < o; i++) a[i] = red_dyn(op[k], a[i], a[i + o]);
+      BSC(b, slot[k]) = a[0];
+    }
+  }
+}
+
 __device__ __noinline__ void p_init(const Args &P, int b, double *scratch) {
   __shared__ double cc_s, sig_s;
   const int n = P.n, m = P.m, tid = threadIdx.x;
@@ -162,7 +196,7 @@ __device__ __noinline__ void p_init(const Args &P, int b, double *scratch) {
 }
 
 // compute_residuals (iteration.c:24-48) + candidate active set (newton.c:122-149) + m-side termination reductions
-__device__ __noinline__ void p_res_m(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_res_m(const Args &P, int b, double *part) {
   const int m = P.m, scaling = P.st.scaling;
   const size_t om = (size_t)b * m;
   double r_pri = 0, r_raw = 0, r_ax = 0, r_z = 0, r_edy = 0, oob = 0, adx_max = -1.0e300, adx_min = 1.0e300;
@@ -192,10 +226,10 @@ __device__ __noinline__ void p_res_m(const Args &P, int b, double *scratch) {
     if (hi_fin) adx_max = fmax(adx_max, adx);
     if (lo_fin) adx_min = fmin(adx_min, adx);
   }
-  RED_OUT(RED_MAX, r_pri, S_PRI_RES) RED_OUT(RED_MAX, r_raw, S_PRI_RES_RAW) RED_OUT(RED_MAX, r_ax, S_NORM_AX)
-  RED_OUT(RED_MAX, r_z, S_NORM_Z) RED_OUT(RED_MAX, r_edy, S_NORM_EDY) RED_OUT(RED_SUM, oob, S_OOB)
-  RED_OUT(RED_MAX, adx_max, S_ADX_MAX) RED_OUT(RED_MIN, adx_min, S_ADX_MIN) RED_OUT(RED_SUM, n_act, S_NB_ACTIVE)
-  RED_OUT(RED_SUM, n_ent, S_NB_ENTER) RED_OUT(RED_SUM, n_lea, S_NB_LEAVE)
+  const double vals[11] = {r_pri, r_raw, r_ax, r_z, r_edy, oob, adx_max, adx_min, n_act, n_ent, n_lea};
+  const int ops[11] = {RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_SUM, RED_MAX, RED_MIN, RED_SUM, RED_SUM, RED_SUM};
+  const int slots[11] = {S_PRI_RES, S_PRI_RES_RAW, S_NORM_AX, S_NORM_Z, S_NORM_EDY, S_OOB, S_ADX_MAX, S_ADX_MIN, S_NB_ACTIVE, S_NB_ENTER, S_NB_LEAVE};
+  block_red_multi<11>(P, b, vals, ops, slots, part);
 }
 
 // out[i] = scale * sum_k M[i + ld*k] v[k], i < nrows (row sums of a shared column-major matrix: A'yh, Q d and, with the
@@ -273,7 +307,7 @@ __device__ __forceinline__ void p_gemv_cols(int len, int ncols, int ld, const do
   }
 }
 
-__device__ __noinline__ void p_res_n(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_res_n(const Args &P, int b, double *part) {
   const int n = P.n;
   const BSet &st = P.st;
   const size_t on = (size_t)b * n;
@@ -303,9 +337,10 @@ __device__ __noinline__ void p_res_n(const Args &P, int b, double *scratch) {
     else dxqdx += P.Qd[on + j] * dx;
     qdx += qj * dx;
   }
-  RED_OUT(RED_MAX, r_dua, S_DUA_RES) RED_OUT(RED_MAX, r_dua2, S_DUA2_RES) RED_OUT(RED_MAX, r_qx, S_NORM_QX)
-  RED_OUT(RED_MAX, r_q, S_NORM_Q) RED_OUT(RED_MAX, r_atyh, S_NORM_ATYH) RED_OUT(RED_MAX, r_atdy, S_NORM_ATDY)
-  RED_OUT(RED_MAX, r_ddx, S_NORM_DDX) RED_OUT(RED_SUM, dxdx, S_DXDX) RED_OUT(RED_SUM, dxqdx, S_DXQDX) RED_OUT(RED_SUM, qdx, S_QDX)
+  const double vals[10] = {r_dua, r_dua2, r_qx, r_q, r_atyh, r_atdy, r_ddx, dxdx, dxqdx, qdx};
+  const int ops[10] = {RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_SUM, RED_SUM, RED_SUM};
+  const int slots[10] = {S_DUA_RES, S_DUA2_RES, S_NORM_QX, S_NORM_Q, S_NORM_ATYH, S_NORM_ATDY, S_NORM_DDX, S_DXDX, S_DXQDX, S_QDX};
+  block_red_multi<10>(P, b, vals, ops, slots, part);
 }
 
 // the control flow of qpalm_solve for one iteration (src/qpalm.c:484-711), executed by one thread
@@ -372,7 +407,7 @@ __device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
     c.beta = st.proximal ? 1.0 / c.gamma : 0.0;
     const double rank_limit = fmin(st.max_rank_update_fraction * (double)(n + m), (double)st.max_rank_update);
     c.scratch = 0;
-    if ((c.reset_newton && na) || (double)(ne + nl) > rank_limit) { f.refac = 1; f.factor = 1; c.scratch = c.reset_newton || !c.H_valid; }
+    if ((c.reset_newton && na) || (double)(ne + nl) > rank_limit) { f.refac = 1; f.factor = 1; c.scratch = (c.reset_newton && !st.batch_h_incremental) || !c.H_valid; }
     else if (na) {   // newton.c:103-108: rank update of the factor (entering rows, then leaving rows)
       if (ne + nl > 0) { if (st.batch_updown) f.updown = 1; else { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
     }
@@ -471,11 +506,25 @@ __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, cons
       ra[t] = i0 + 8 * t + fr; if (ra[t] >= n) ra[t] = n - 1;
       rb[t] = j0 + 8 * t + fr; if (rb[t] >= n) rb[t] = n - 1;
     }
-    double acc[2][2][2];
+    // the old values of the tile are requested BEFORE the product loop, so their L2 / DRAM latency hides under it (a
+    // read-modify-write after the loop left every warp on the long scoreboard: 15 % of the kernel's stall samples in
+    // profiles/r02f_ncu_source_kbp_solve.txt); the arithmetic is unchanged (base + sign * sum)
+    double acc[2][2][2], base[2][2][2];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) acc[a][e][0] = acc[a][e][1] = 0.0;
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          acc[a][e][h] = 0.0;
+          const int i = i0 + 8 * a + fr, j = j0 + 8 * e + 2 * fk + h;
+          double bv = 0.0;
+          if (i < n && j < n && i >= j) {
+            if (first) { bv = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) bv += diag_add; }
+            else bv = dst[(size_t)i + (size_t)ldd * j];
+          }
+          base[a][e][h] = bv;
+        }
     for (int kc = 0; kc < wpad; kc += 4) {
       const int c = kc + fk;
       const bool live = c < w;
@@ -495,14 +544,30 @@ __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, cons
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int i = i0 + 8 * a + fr, j = j0 + 8 * e + 2 * fk + h;
-          if (i < n && j < n && i >= j) {
-            double base;
-            if (first) { base = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) base += diag_add; }
-            else base = dst[(size_t)i + (size_t)ldd * j];
-            dst[(size_t)i + (size_t)ldd * j] = fma(sign, acc[a][e][h], base);
-          }
+          if (i < n && j < n && i >= j) dst[(size_t)i + (size_t)ldd * j] = fma(sign, acc[a][e][h], base[a][e][h]);
         }
   }
+}
+
+// cp.async (LDGSTS) 8-byte copy global -> shared.  A panel load requests ALL its elements before anything waits and holds
+// no registers; the former `Pn[..] = L[..]` loop kept one or two loads in flight per thread and sat on the long scoreboard
+// (the per-instance factors do not fit the L2: 15 % of the kernel's stall samples, profiles/r02f_ncu_source_kbp_solve.txt).
+__device__ __forceinline__ void bp_cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Pn[t][r] <- L(k0 + r, k0 + t) for t <= r < rows, t < w; zeros above the diagonal of the w x w block.  Rows fastest (coalesced).
+// The caller's __syncthreads() publishes the panel.
+__device__ __forceinline__ void panel_load_async(double *Pn, const double *L, int ld, int k0, int w, int rows) {
+  for (int t = 0; t < w; t++) {
+    const double *col = L + (size_t)k0 + (size_t)ld * (k0 + t);
+    for (int r = threadIdx.x; r < rows; r += NT) {
+      if (r >= t) bp_cp_async8(&Pn[t * LDP + r], col + r);
+      else Pn[t * LDP + r] = 0.0;
+    }
+  }
+  bp_cp_async_wait_all();
 }
 
 // The PW = 32 column panel is factorised as two 16-column sub-panels so that every per-thread register array is 16
@@ -623,16 +688,14 @@ __device__ __forceinline__ void cta_potrf(double *L, int ld, const double *src, 
   for (int k0 = 0; k0 < n; k0 += PW) {
     const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
     const bool first = (k0 == 0);
-    for (int idx = tid; idx < w * rows; idx += NT) {   // panel load, rows fastest (coalesced)
-      const int t = idx / rows, r = idx - t * rows;
-      const int i = k0 + r, j = k0 + t;
-      double v = 0.0;
-      if (r >= t) {
-        if (first) { v = sscale * src[(size_t)i + (size_t)lds * j]; if (i == j) v += beta; }
-        else v = L[(size_t)i + (size_t)ld * j];
+    if (first) {
+      for (int idx = tid; idx < w * rows; idx += NT) {   // panel load, rows fastest (coalesced)
+        const int t = idx / rows, r = idx - t * rows;
+        double v = 0.0;
+        if (r >= t) { v = sscale * src[(size_t)r + (size_t)lds * t]; if (r == t) v += beta; }
+        Pn[t * LDP + r] = v;
       }
-      Pn[t * LDP + r] = v;
-    }
+    } else panel_load_async(Pn, L, ld, k0, w, rows);
     __syncthreads();
     PQ(16);
     if (tid < 32) warp_factor_diag16(Pn, S.rd, 0, w, info);
@@ -676,10 +739,7 @@ __device__ __forceinline__ void cta_chol_solve(const double *L, int ld, int n, c
   if (!skip_forward) {
     for (int k0 = 0; k0 < n; k0 += PW) {   // forward: L z = v
       const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
-      for (int idx = tid; idx < w * rows; idx += NT) {
-        const int t = idx / rows, r = idx - t * rows;
-        Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
-      }
+      panel_load_async(Pn, L, ld, k0, w, rows);
       if (tid < w) S.rd[tid] = rdiag_g[k0 + tid];
       __syncthreads();
       panel_forward(Pn, v, S.rd, k0, w, rows);
@@ -689,10 +749,7 @@ __device__ __forceinline__ void cta_chol_solve(const double *L, int ld, int n, c
   const int last = ((n - 1) / PW) * PW;
   for (int k0 = last; k0 >= 0; k0 -= PW) {
     const int w = (n - k0 < PW) ? n - k0 : PW, rows = n - k0;
-    for (int idx = tid; idx < w * rows; idx += NT) {
-      const int t = idx / rows, r = idx - t * rows;
-      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
-    }
+    panel_load_async(Pn, L, ld, k0, w, rows);
     __syncthreads();
     for (int t = warp; t < w; t += NW) {   // v[k0 + t] -= sum_{r >= w} L(k0 + r, k0 + t) d(k0 + r)
       double s = 0.0;
@@ -769,10 +826,7 @@ __device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += UW) {
     const int w = (n - k0 < UW) ? n - k0 : UW, rows = n - k0;
-    for (int idx = tid; idx < w * rows; idx += NT) {   // panel load, rows fastest (coalesced)
-      const int t = idx / rows, r = idx - t * rows;
-      Pn[t * LDP + r] = (r >= t) ? L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] : 0.0;
-    }
+    panel_load_async(Pn, L, ld, k0, w, rows);
     __syncthreads();
     if (warp == 0) {   // the recurrence on the diagonal block: lane = block row (w of them) AND lane = rank (k of them)
       double wl[KU];
@@ -1043,7 +1097,7 @@ __device__ __noinline__ void p_boost(const Args &P, int b, double *scratch, cons
 // ------------------------------------------------------------------------------------------------
 // line search (linesearch.c:14-120)
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void p_ls_build(const Args &P, int b, double *scratch) {
+__device__ __noinline__ void p_ls_build(const Args &P, int b, double *part) {
   const int n = P.n, m = P.m;
   const size_t on = (size_t)b * n, om = (size_t)b * m, o2 = (size_t)b * 2 * m;
   const double inv_gamma = 1 / P.ctl[b].gamma;
@@ -1076,8 +1130,10 @@ __device__ __noinline__ void p_ls_build(const Args &P, int b, double *scratch) {
       n_l += inL;
     }
   }
-  RED_OUT(RED_SUM, eta, S_ETA) RED_OUT(RED_SUM, beta, S_BETA) RED_OUT(RED_SUM, a_part, S_LS_A)
-  RED_OUT(RED_SUM, b_part, S_LS_B) RED_OUT(RED_SUM, n_l, S_NL)
+  const double vals[5] = {eta, beta, a_part, b_part, n_l};
+  const int ops[5] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+  const int slots[5] = {S_ETA, S_BETA, S_LS_A, S_LS_B, S_NL};
+  block_red_multi<5>(P, b, vals, ops, slots, part);
 }
 
 // stable LSD radix sort of N <= SORT_MAX (key, val) pairs in shared memory; sorted pairs are written back to global
@@ -1265,13 +1321,13 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
     PH(0);
     for (;;) {
       // ---- residuals + termination scalars ----
-      p_res_m(P, b, scratch);
+      p_res_m(P, b, S.vs);
       __syncthreads();
       PH(1);
       p_gemv_rows(n, m, n, P.At, P.yh + om, P.Atyh + on, 1.0, S);
       __syncthreads();
       PH(2);
-      p_res_n(P, b, scratch);
+      p_res_n(P, b, S.vs);
       __syncthreads();
       if (tid == 0) p_control(P, b, s_f);
       __syncthreads();
@@ -1345,7 +1401,7 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
         p_gemv_rows(m, n, m, P.Am, P.d + on, P.Ad + om, 1.0, S);
         __syncthreads();
         PH(9);
-        p_ls_build(P, b, scratch);
+        p_ls_build(P, b, S.vs);
         __syncthreads();
         PH(10);
         p_sort(2 * m, P.keys + (size_t)b * 2 * m, P.vals + (size_t)b * 2 * m, S);
