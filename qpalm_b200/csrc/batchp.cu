@@ -803,117 +803,250 @@ __device__ __forceinline__ void cta_syrk_list(double *dst, int ld, int n, const 
 // 16 x 16 diagonal block (its rows of W in registers) and leaves the column coefficients in shared memory, then every thread
 // transforms one row below the block.
 // ------------------------------------------------------------------------------------------------
-constexpr int KU = 8, UW = 16;
-static_assert((UW + KU) * LDP * sizeof(double) <= kUnionBytes, "update panel + W block must fit the union region");
+constexpr int KU = 8, UW = 16, WIN = 32, PBL = 33;   // ranks per sweep, columns per block, rows of the chain warp's window, block row pitch
+constexpr int NRING = 3;                              // window-block buffers: in use by the chain / being requested / being written back
+constexpr int LVW = 8;                                // row owners: columns of their row's entries in flight (shared-memory staging ring)
+static_assert((KU * LDP + NRING * UW * PBL + LVW * LDP) * sizeof(double) <= kUnionBytes,
+              "W block + the ring of window-block buffers + the row owners' staging ring must fit the union region");
 
-struct UdCoef {   // in S.vs
-  double winv[UW], lnew[UW], wj[UW][KU], gam[UW][KU], ialpha[KU], wrow[32][KU + 1];
+struct UdCoef {   // in S.vs: the coefficients of one 16-column block, written column by column by the chain warp
+  double winv[UW], dfin[2][UW];   // dfin by block parity: the previous block's new pivots are still needed while it is written back
+  __align__(16) double wj[UW][KU];
+  __align__(16) double gam[UW][KU];
+  double wrow[32][KU + 1];
 };
 static_assert(sizeof(UdCoef) <= sizeof(double) * VS_LEN, "update coefficients must fit the staged-vector buffer");
 
+__device__ __forceinline__ void ud_mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+// arrive by lane 0 only, as a PREDICATED instruction (a branch would split the chain warp, see the note in the column loop)
+__device__ __forceinline__ void ud_mbar_arrive_lane0(unsigned long long *bar, int lane) {
+  asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(lane) : "memory");
+}
+__device__ __forceinline__ void ud_mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+#ifdef QB_UD_TESTWAIT
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
+#else
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+__device__ __forceinline__ void bp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bp_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// chain warp: request the 32 x 16 window block at (k0, k0) -- lane = row k0 + lane, columns c <= lane -- into Pb[c * PBL + lane]
+__device__ __forceinline__ void ud_block_prefetch(double *Pb, const double *L, int ld, int k0, int n, int lane) {
+  const int row = k0 + lane;
+#pragma unroll
+  for (int c = 0; c < UW; c++) {
+    if (row < n && k0 + c < n && c <= lane) bp_cp_async8(&Pb[c * PBL + lane], L + (size_t)row + (size_t)ld * (k0 + c));
+    else Pb[c * PBL + lane] = 0.0;
+  }
+  bp_cp_async_commit();
+}
+
 // one sweep: L <- chol(L L' + sum_{r < kpos} w_r w_r' - sum_{kpos <= r < k} w_r w_r'),  w_r = wgt[r] * A'[:, list[r]]
+//
+// Round-2 shape (profiles/r02f_ncu_source_kbp_solve.txt: the old panel-staged sweep spent 18 % of the kernel with seven warps parked
+// on the barrier behind warp 0's recurrence and another 12 % loading / storing panels):
+//   * the CHAIN WARP (warp 0) walks the diagonal.  Its 32 lanes are the rows k0 .. k0 + 31 of the current 16-column block (the 16 block
+//     rows and 16 look-ahead rows); their L entries sit in a small shared buffer that was requested one block ahead (cp.async), their
+//     rows of W in registers.  Per column it forms the (alpha, gamma) coefficients, publishes them and arrives on that column's mbarrier.
+//   * every other thread owns ONE row of L for the whole sweep (thread t <-> row t), keeps that row of W in registers and its 16
+//     entries of the current block in registers (loaded straight from global memory before the block starts, written straight back):
+//     it waits on the column's mbarrier, applies the column, and so trails the chain warp by one column.  The rows-below pass, the
+//     panel staging and two of the four barriers per block are gone; what remains per block is the chain itself.
+// The arithmetic per row is unchanged (t = l / l_jj; { w_r -= w_r[j] t; t -= gamma_r w_r }; l' = t sqrt(d_k)).
+// bars: UW mbarriers (count 1) initialised once per kernel; every block completes exactly one phase of each; phase = blocks so far.
+// block-end rendezvous of the two roles (named barrier 1; __syncthreads() is barrier 0 and is used by the code around the sweep)
+__device__ __forceinline__ void ud_block_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+// write the finished window block (rows k0 .. k0 + 31, columns k0 .. k0 + 15; unit-scaled entries in Pn, new pivots squared in dfin)
+// back to L: l' = t sqrt(d_k), l_jj' = sqrt(d_k), rdiag = 1 / l_jj'.  Called by `nthr` threads with t = 0 .. nthr - 1.
+__device__ __forceinline__ void ud_flush_block(double *L, int ld, int n, double *rdiag_g, int k0, const double *Pn, const double *dfin, int t, int nthr) {
+  const int w = (n - k0 < UW) ? n - k0 : UW;
+  for (int e = t; e < WIN * UW; e += nthr) {
+    const int l = e & (WIN - 1), c = e / WIN;
+    if (c < w && k0 + l < n && l >= c) {
+      const double ln = sqrt(dfin[c]);
+      L[(size_t)(k0 + l) + (size_t)ld * (k0 + c)] = (l == c) ? ln : Pn[c * PBL + l] * ln;
+      if (l == c) rdiag_g[k0 + c] = 1.0 / ln;
+    }
+  }
+}
+
+// role 1 of the sweep: the chain warp (warp 0).  Nothing but the recurrence: its window blocks are requested and written back by
+// the row owners (a first version did both here and spent 40 % of every block outside the column loop).
+__device__ __forceinline__ void ud_chain_role(int n, int k, int kpos, double *Wm, double *Pb0, UdCoef &cf, int *info, unsigned long long *bars,
+                                              long long *pf) {
+  const int lane = threadIdx.x & 31;
+  long long tq = clock64();
+#define PC(k) do { if (pf) { const long long t_ = clock64(); if (lane == 31) atomicAdd(reinterpret_cast<unsigned long long *>(pf + (k)), (unsigned long long)(t_ - tq)); tq = t_; } } while (0)
+  double ial = 1.0;                          // lane r < k: 1 / alpha_r
+  const double sg = (lane < kpos) ? 1.0 : -1.0;
+  bool bad = false;
+  int slot = 0, blk = 0;
+  for (int k0 = 0; k0 < n; k0 += UW, slot = (slot + 1 == NRING) ? 0 : slot + 1, blk++) {
+    const int w = (n - k0 < UW) ? n - k0 : UW;
+    double *Pn = Pb0 + slot * (UW * PBL);
+    double *dfin_out = cf.dfin[blk & 1];
+    const bool rowvalid = k0 + lane < n;
+    double wl[KU];
+#pragma unroll
+    for (int r = 0; r < KU; r++) wl[r] = rowvalid ? Wm[r * LDP + k0 + lane] : 0.0;
+    // off the chain: the old pivots are not touched before their own column, so 1 / l_jj and l_jj^2 of all 16 columns are
+    // formed up front (lane = column); the new pivots sqrt(d) and the column scaling are left to the write-back
+    const double ldiag = (lane < w) ? Pn[lane * PBL + lane] : 1.0;
+    const double winv_l = 1.0 / ldiag, d0_l = ldiag * ldiag;
+    __syncwarp();
+    PC(23);
+    // The loop body has NO divergent region (a warp that splits pays the slow collective path on every later shuffle):
+    // every lane publishes its row of W each column, stale rows (<= j) keep computing on dead values, stores are predicated.
+    for (int j = 0; j < w; j++) {
+#pragma unroll
+      for (int r = 0; r < KU; r++) cf.wrow[lane][r] = wl[r];
+      const double winv = __shfl_sync(0xffffffffu, winv_l, j), d0 = __shfl_sync(0xffffffffu, d0_l, j);
+      __syncwarp();
+      const double wj = (lane < k) ? cf.wrow[j][lane & (KU - 1)] : 0.0;
+      const double c = sg * wj * wj * ial;
+      double incl = c;
+#pragma unroll
+      for (int off = 1; off < KU; off <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += up;
+      }
+      const double dnext = d0 + incl, dprev = d0 + (incl - c);
+      if (lane < k && !(dnext > 0.0)) bad = true;
+      double q;   // ial / dnext: reciprocal seed + two Newton steps instead of the IEEE division subroutine
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(dnext));
+      q = fma(q, fma(-dnext, q, 1.0), q);
+      q = fma(q, fma(-dnext, q, 1.0), q);
+      q *= ial;
+      const double gam = -sg * wj * q;
+      ial = dprev * q;
+      const double dfin = __shfl_sync(0xffffffffu, dnext, k - 1);
+      {   // publish column j (stores predicated by value selection, no branch: lanes < KU write the rank coefficients, lane KU the scalars)
+        const bool rk = lane < KU;
+        double *p0 = rk ? &cf.wj[j][lane] : &cf.winv[j], *p1 = rk ? &cf.gam[j][lane] : &dfin_out[j];
+        const double v0 = rk ? ((lane < k) ? wj : 0.0) : winv, v1 = rk ? ((lane < k) ? gam : 0.0) : dfin;
+        if (lane <= KU) { *p0 = v0; *p1 = v1; }
+      }
+      __syncwarp();
+      ud_mbar_arrive_lane0(bars + j, lane);   // column j is published: the row owners may apply it
+      {
+        double t = (rowvalid ? Pn[j * PBL + lane] : 0.0) * winv;
+#pragma unroll
+        for (int r = 0; r < KU; r++) {
+          wl[r] = fma(-cf.wj[j][r], t, wl[r]);
+          t = fma(-cf.gam[j][r], wl[r], t);
+        }
+        if (lane > j && rowvalid) Pn[j * PBL + lane] = t;   // unit-scaled; the write-back multiplies by the new pivot
+      }
+      __syncwarp();
+    }
+    PC(25);
+    for (int j = w; j < UW; j++) ud_mbar_arrive_lane0(bars + j, lane);   // ragged last block: every barrier completes one phase per block
+    if (lane >= UW && rowvalid) {   // the look-ahead rows are block rows of the next window: hand their W over
+#pragma unroll
+      for (int r = 0; r < KU; r++) Wm[r * LDP + k0 + lane] = wl[r];
+    }
+    __syncwarp();
+    PC(26);
+    ud_block_barrier();
+    PC(27);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) *info = 1;
+#undef PC
+}
+
+// role 2 of the sweep: a row owner (threads >= WIN; thread t <-> row t).  Besides its own row it helps the chain warp: the previous
+// window block is written back by all row owners, the next one is requested by warp 1.
+__device__ __forceinline__ void ud_row_role(double *L, int ld, int n, double *rdiag_g, double *Wm, double *Pb0, double *Ls, const UdCoef &cf,
+                                            unsigned long long *bars, unsigned phase) {
+  const int row = threadIdx.x, lane = threadIdx.x & 31;
+  const bool requester = (threadIdx.x >> 5) == 1;
+  double wv[KU];
+#pragma unroll
+  for (int r = 0; r < KU; r++) wv[r] = (row < n) ? Wm[r * LDP + row] : 0.0;
+  int slot = 0, blk = 0;
+  // This row's entries of the block travel through a private staging ring in shared memory: Ls[c % LVW][row] is written by this
+  // thread's own cp.async and read by this thread only, so no barrier is involved and no registers are held (16 entries in
+  // registers spill at 64 registers per thread, and a spilled entry costs an L2 round trip per column).  Entry c + LVW (of this or
+  // the next block) is requested as soon as entry c has been consumed, i.e. LVW columns ahead of its use.
+  if (row >= WIN && row < n) {
+#pragma unroll
+    for (int c = 0; c < LVW; c++) {
+      if (c < n) bp_cp_async8(&Ls[c * LDP + row], L + (size_t)row + (size_t)ld * c);
+      bp_cp_async_commit();
+    }
+  }
+  for (int k0 = 0; k0 < n; k0 += UW, slot = (slot + 1 == NRING) ? 0 : slot + 1, blk++) {
+    const int w = (n - k0 < UW) ? n - k0 : UW;
+    const unsigned par = phase & 1u;
+    phase++;
+    const int slot_next = (slot + 1 == NRING) ? 0 : slot + 1, slot_prev = (slot == 0) ? NRING - 1 : slot - 1;
+    const bool below = row >= k0 + WIN && row < n, below_next = row >= k0 + UW + WIN && row < n;
+    double *Lr = L + (size_t)row + (size_t)ld * k0;
+    const double *dfin = cf.dfin[blk & 1];
+    if (requester && k0 + UW < n) ud_block_prefetch(Pb0 + slot_next * (UW * PBL), L, ld, k0 + UW, n, lane);
+    if (k0 > 0) ud_flush_block(L, ld, n, rdiag_g, k0 - UW, Pb0 + slot_prev * (UW * PBL), cf.dfin[(blk - 1) & 1], threadIdx.x - WIN, NT - WIN);
+    if (below) {   // below the window: apply the block column by column as it is published
+#pragma unroll
+      for (int c = 0; c < UW; c++) {
+        if (c < w) {
+          bp_cp_async_wait_group<LVW - 1>();   // this thread's request for column c has landed (later groups may still be in flight)
+          ud_mbar_wait(bars + c, par);
+          double t = Ls[(c % LVW) * LDP + row] * cf.winv[c];
+          const double2 *wj2 = reinterpret_cast<const double2 *>(cf.wj[c]), *gm2 = reinterpret_cast<const double2 *>(cf.gam[c]);
+#pragma unroll
+          for (int r2 = 0; r2 < KU / 2; r2++) {
+            const double2 a = wj2[r2], g = gm2[r2];
+            wv[2 * r2] = fma(-a.x, t, wv[2 * r2]);
+            t = fma(-g.x, wv[2 * r2], t);
+            wv[2 * r2 + 1] = fma(-a.y, t, wv[2 * r2 + 1]);
+            t = fma(-g.y, wv[2 * r2 + 1], t);
+          }
+          Lr[(size_t)ld * c] = t * sqrt(dfin[c]);
+        }
+        // refill the slot just consumed: column c + LVW of this block, or of the next block when this row stays below the window
+        const int cn = c + LVW;
+        if ((cn < UW || below_next) && k0 + cn < n) bp_cp_async8(&Ls[(c % LVW) * LDP + row], Lr + (size_t)ld * cn);
+        bp_cp_async_commit();
+      }
+      if (row < k0 + WIN + UW) {   // this row enters the chain warp's window with the next block: hand its W over
+#pragma unroll
+        for (int r = 0; r < KU; r++) Wm[r * LDP + row] = wv[r];
+      }
+    }
+    if (requester) bp_cp_async_wait_group<0>();
+    ud_block_barrier();
+  }
+}
+
 __device__ __noinline__ void cta_updown_sweep(double *L, int ld, int n, double *rdiag_g, const double *__restrict__ At,
-                                              const int *__restrict__ list, const double *__restrict__ wgt, int k, int kpos, const Smem &S, int *info) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double *Pn = S.panel, *Wm = S.panel + UW * LDP;
+                                              const int *__restrict__ list, const double *__restrict__ wgt, int k, int kpos, const Smem &S, int *info,
+                                              unsigned long long *bars, unsigned &phase, long long *pf) {
+  const int tid = threadIdx.x;
+  double *Wm = S.panel, *Pb0 = S.panel + KU * LDP;
   UdCoef &cf = *reinterpret_cast<UdCoef *>(S.vs);
+  long long tq = clock64();
+#define PQ(k) do { if (pf) { const long long t_ = clock64(); if (tid == NT - 1) atomicAdd(reinterpret_cast<unsigned long long *>(pf + (k)), (unsigned long long)(t_ - tq)); tq = t_; } } while (0)
   for (int idx = tid; idx < KU * n; idx += NT) {   // gather the rows (zero columns beyond k)
     const int r = idx / n, i = idx - r * n;
     Wm[r * LDP + i] = (r < k) ? wgt[r] * At[(size_t)i + (size_t)n * list[r]] : 0.0;
   }
-  if (tid < KU) cf.ialpha[tid] = 1.0;
-  for (int idx = tid; idx < UW * KU; idx += NT) { cf.wj[0][idx] = 0.0; cf.gam[0][idx] = 0.0; }
+  if (tid < 32) { ud_block_prefetch(Pb0, L, ld, 0, n, tid); bp_cp_async_wait_group<0>(); }
   __syncthreads();
-  for (int k0 = 0; k0 < n; k0 += UW) {
-    const int w = (n - k0 < UW) ? n - k0 : UW, rows = n - k0;
-    panel_load_async(Pn, L, ld, k0, w, rows);
-    __syncthreads();
-    if (warp == 0) {   // the recurrence on the diagonal block: lane = block row (w of them) AND lane = rank (k of them)
-      double wl[KU];
-#pragma unroll
-      for (int r = 0; r < KU; r++) wl[r] = (lane < w) ? Wm[r * LDP + k0 + lane] : 0.0;
-      double ial = (lane < KU) ? cf.ialpha[lane] : 1.0;
-      const double sg = (lane < kpos) ? 1.0 : -1.0;
-      bool bad = false;
-      // off the chain: the old pivots are not touched before their own column, so 1 / l_jj and l_jj^2 of all 16 columns are
-      // formed up front (lane = column), and the new pivots sqrt(d) and the column scaling wait until after the loop
-      const double ldiag = (lane < w) ? Pn[lane * LDP + lane] : 1.0;
-      const double winv_l = 1.0 / ldiag, d0_l = ldiag * ldiag;
-      double dfin_l = 1.0;
-      __syncwarp();
-      // The loop body has NO divergent region (a warp that splits pays the slow collective path on every later shuffle):
-      // every lane publishes its row of W each column, stale rows (<= j) keep computing on dead values, stores are predicated.
-      for (int j = 0; j < w; j++) {
-#pragma unroll
-        for (int r = 0; r < KU; r++) cf.wrow[lane][r] = wl[r];
-        const double winv = __shfl_sync(0xffffffffu, winv_l, j), d0 = __shfl_sync(0xffffffffu, d0_l, j);
-        __syncwarp();
-        const double wj = (lane < k) ? cf.wrow[j][lane & (KU - 1)] : 0.0;
-        const double c = sg * wj * wj * ial;
-        double incl = c;
-#pragma unroll
-        for (int off = 1; off < KU; off <<= 1) {
-          const double up = __shfl_up_sync(0xffffffffu, incl, off);
-          if (lane >= off) incl += up;
-        }
-        const double dnext = d0 + incl, dprev = d0 + (incl - c);
-        if (lane < k && !(dnext > 0.0)) bad = true;
-        double q;   // ial / dnext: reciprocal seed + two Newton steps instead of the IEEE division subroutine
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(dnext));
-        q = fma(q, fma(-dnext, q, 1.0), q);
-        q = fma(q, fma(-dnext, q, 1.0), q);
-        q *= ial;
-        const double gam = -sg * wj * q;
-        ial = dprev * q;
-        const double dfin = __shfl_sync(0xffffffffu, dnext, k - 1);
-        if (lane == j) dfin_l = dfin;
-        if (lane < k) { cf.wj[j][lane] = wj; cf.gam[j][lane] = gam; }
-        __syncwarp();
-        {
-          double t = ((lane < w) ? Pn[j * LDP + lane] : 0.0) * winv;   // predicated load: lanes beyond the block read nothing
-#pragma unroll
-          for (int r = 0; r < KU; r++) {
-            wl[r] = fma(-cf.wj[j][r], t, wl[r]);
-            t = fma(-cf.gam[j][r], wl[r], t);
-          }
-          if (lane > j && lane < w) Pn[j * LDP + lane] = t;   // still unit-scaled; multiplied by the new pivot below
-        }
-        __syncwarp();
-      }
-      const double lnew_l = sqrt(dfin_l);
-      if (lane < w) { cf.winv[lane] = winv_l; cf.lnew[lane] = lnew_l; Pn[lane * LDP + lane] = lnew_l; }
-      for (int j = 0; j < w; j++) {
-        const double lj = __shfl_sync(0xffffffffu, lnew_l, j);
-        if (lane > j && lane < w) Pn[j * LDP + lane] *= lj;
-      }
-      if (lane < KU) cf.ialpha[lane] = ial;
-      if (__any_sync(0xffffffffu, bad) && lane == 0) *info = 1;
-    }
-    __syncthreads();
-    for (int rr = w + tid; rr < rows; rr += NT) {   // rows below the block: one row per thread
-      double wv[KU];
-#pragma unroll
-      for (int r = 0; r < KU; r++) wv[r] = Wm[r * LDP + k0 + rr];
-      for (int c = 0; c < w; c++) {
-        double t = Pn[c * LDP + rr] * cf.winv[c];
-#pragma unroll
-        for (int r = 0; r < KU; r++) {
-          wv[r] = fma(-cf.wj[c][r], t, wv[r]);
-          t = fma(-cf.gam[c][r], wv[r], t);
-        }
-        Pn[c * LDP + rr] = t * cf.lnew[c];
-      }
-#pragma unroll
-      for (int r = 0; r < KU; r++) Wm[r * LDP + k0 + rr] = wv[r];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < w * rows; idx += NT) {
-      const int t = idx / rows, r = idx - t * rows;
-      if (r >= t) L[(size_t)(k0 + r) + (size_t)ld * (k0 + t)] = Pn[t * LDP + r];
-    }
-    if (tid < w) rdiag_g[k0 + tid] = 1.0 / cf.lnew[tid];
-    __syncthreads();
-  }
+  PQ(22);
+  if (tid < 32) ud_chain_role(n, k, kpos, Wm, Pb0, cf, info, bars, pf);
+  else ud_row_role(L, ld, n, rdiag_g, Wm, Pb0, Pb0 + NRING * UW * PBL, cf, bars, phase);
+  const int nblk = (n + UW - 1) / UW;
+  phase += (unsigned)nblk;
+  ud_flush_block(L, ld, n, rdiag_g, (nblk - 1) * UW, Pb0 + ((nblk - 1) % NRING) * (UW * PBL), cf.dfin[(nblk - 1) & 1], tid, NT);   // last window block
+  __syncthreads();
+  PQ(24);
+#undef PQ
 }
 
 // ordered lists of the entering (candidate active, not in the factor) and leaving rows, entering first, weights sqrt(sigma):
@@ -1298,6 +1431,13 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
   __shared__ int s_b;
   __shared__ Flags s_f;
   __shared__ int s_info;
+  __shared__ __align__(8) unsigned long long s_udbar[UW];   // per-column mbarriers of the update sweep (chain warp -> row owners)
+  unsigned ud_phase = 0;
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < UW; j++) ud_mbar_init(s_udbar + j, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   Smem S;
   S.u = smem_raw;
   S.panel = reinterpret_cast<double *>(smem_raw);
@@ -1351,7 +1491,8 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
           for (int off = 0; off < ne + nl; off += KU) {
             const int k = (ne + nl - off < KU) ? ne + nl - off : KU;
             const int kpos = (ne - off < 0) ? 0 : ((ne - off < k) ? ne - off : k);
-            cta_updown_sweep(Lb, ld, n, rdg, P.At, P.list_pos + om + off, P.w_pos + om + off, k, kpos, S, &s_info);
+            cta_updown_sweep(Lb, ld, n, rdg, P.At, P.list_pos + om + off, P.w_pos + om + off, k, kpos, S, &s_info,
+                             s_udbar, ud_phase, P.prof ? P.prof + (size_t)b * 32 : nullptr);
           }
           __syncthreads();
           if (tid == 0) {

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -fmad=false"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -fmad=false $QB_EXTRA_FLAGS"
 mkdir -p build
 pids=()
 for f in dense updown_flow kernels api ops compat kkt batch batchp prof shard sparse sparse_sym qps; do
