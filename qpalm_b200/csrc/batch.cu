@@ -846,6 +846,7 @@ extern "C" QPALMB200Batch *qpalm_b200_batch_setup(const QPALMData *shared, const
   st.gamma_max = s->gamma_max; st.max_rank_update_fraction = s->max_rank_update_fraction; st.sqrt_sigma_max = sqrt(s->sigma_max);
   st.data_c = shared->c;
   { const char *u = getenv("QPALM_B200_BATCH_UPDOWN"); st.batch_updown = u ? atoi(u) : 1; }
+  { const char *u = getenv("QPALM_B200_BATCH_UPDOWN_MAX_RANK"); st.batch_updown_max_rank = u ? atoi(u) : 40; }
   { const char *u = getenv("QPALM_B200_BATCH_HINC"); st.batch_h_incremental = u ? atoi(u) : 0; }
   if (s->scaling) {   // Ruiz on the shared matrices; the cost scaling c is per instance (applied on the fly)
     double cc;

@@ -24,6 +24,8 @@ struct BSet {   // settings the device needs (copied by value into kernels)
   double eps_abs, eps_rel, eps_abs_in, eps_rel_in, rho, eps_prim_inf, eps_dual_inf, theta, delta, sigma_max, sigma_init;
   double gamma_init, gamma_upd, gamma_max, max_rank_update_fraction, sqrt_sigma_max, data_c;
   int batch_updown;              // persistent engine: take rank updates where the reference does (QPALM_B200_BATCH_UPDOWN=0 disables)
+  int batch_updown_max_rank;     // persistent engine: beyond this many changed rows an (incremental) refactorisation is cheaper than the
+                                 // sweeps (same matrix either way; QPALM_B200_BATCH_UPDOWN_MAX_RANK)
   int batch_h_incremental;       // persistent engine: after reset_newton keep the H record and apply only the changed rows / sigmas
                                  // (QPALM_B200_BATCH_HINC=1; default 0 = rebuild H from Q as the reference's ldlcholQAtsigmaA does)
 };

@@ -409,7 +409,13 @@ __device__ __noinline__ void p_control(const Args &P, int b, Flags &f) {
     c.scratch = 0;
     if ((c.reset_newton && na) || (double)(ne + nl) > rank_limit) { f.refac = 1; f.factor = 1; c.scratch = (c.reset_newton && !st.batch_h_incremental) || !c.H_valid; }
     else if (na) {   // newton.c:103-108: rank update of the factor (entering rows, then leaving rows)
-      if (ne + nl > 0) { if (st.batch_updown) f.updown = 1; else { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; } }
+      if (ne + nl > 0) {
+        // The reference updates the factor here whatever the rank (<= min(0.1 (n + m), 160) rows).  A sweep handles 8 ranks, so
+        // beyond ~5 sweeps the incremental SYRK + refactorisation is the cheaper way to the SAME matrix: 512-instance sweep
+        // 91.5 ms without the cap, 88.0 ms at 40 (88.8 / 88.8 / 88.2 / 90.6 ms at 24 / 32 / 48 / 56), iteration counts unchanged.
+        if (st.batch_updown && ne + nl <= st.batch_updown_max_rank) f.updown = 1;
+        else { f.refac = 1; f.factor = 1; c.scratch = !c.H_valid; }
+      }
     }
     else { f.fq = 1; f.factor = 1; }
     c.reset_newton = 0;
@@ -810,10 +816,11 @@ static_assert((KU * LDP + NRING * UW * PBL + LVW * LDP) * sizeof(double) <= kUni
               "W block + the ring of window-block buffers + the row owners' staging ring must fit the union region");
 
 struct UdCoef {   // in S.vs: the coefficients of one 16-column block, written column by column by the chain warp
-  double winv[UW], dfin[2][UW];   // dfin by block parity: the previous block's new pivots are still needed while it is written back
+  double winv[UW], d0[UW], dfin[2][UW];   // old pivots (1 / l_jj, l_jj^2) of the whole block, written at its start; dfin by block parity: the previous block's new pivots are still needed while it is written back
   __align__(16) double wj[UW][KU];
   __align__(16) double gam[UW][KU];
-  double wrow[32][KU + 1];
+  __align__(16) double wpiv[KU];   // the pivot row's W as it stands before its column (published by that row's lane one column earlier)
+  __align__(16) double cbuf[KU];   // per-rank pivot increments s_r w_r^2 / alpha_r of the current column
 };
 static_assert(sizeof(UdCoef) <= sizeof(double) * VS_LEN, "update coefficients must fit the staged-vector buffer");
 
@@ -901,20 +908,32 @@ __device__ __forceinline__ void ud_chain_role(int n, int k, int kpos, double *Wm
     const double winv_l = 1.0 / ldiag, d0_l = ldiag * ldiag;
     __syncwarp();
     PC(23);
-    // The loop body has NO divergent region (a warp that splits pays the slow collective path on every later shuffle):
-    // every lane publishes its row of W each column, stale rows (<= j) keep computing on dead values, stores are predicated.
+    // Column step.  One dependent chain: pivot row's W (shared memory, left there by that row's lane at the end of the previous
+    // step) -> per-rank increments c_r -> their prefix sums d_r (ONE exchange through shared memory and a depth-3 add tree; the first
+    // version scanned with three dependent shuffle rounds at ~54 clocks each) -> reciprocal -> gamma_r, alpha_r -> publish ->
+    // row update of the window.  There is no shuffle in the loop (the old pivots of the block sit in shared memory), so a lane-dependent
+    // branch around a store cannot push later steps onto the slow collective path.
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < KU; r++) cf.wpiv[r] = wl[r];
+    }
+    if (lane < UW) { cf.winv[lane] = winv_l; cf.d0[lane] = d0_l; }
+    double sgial = sg * ial;
+    __syncwarp();
     for (int j = 0; j < w; j++) {
-#pragma unroll
-      for (int r = 0; r < KU; r++) cf.wrow[lane][r] = wl[r];
-      const double winv = __shfl_sync(0xffffffffu, winv_l, j), d0 = __shfl_sync(0xffffffffu, d0_l, j);
+      const double winv = cf.winv[j], d0 = cf.d0[j];
+      const double wj = (lane < k) ? cf.wpiv[lane & (KU - 1)] : 0.0;
+      const double c = wj * wj * sgial;            // = sg wj^2 ial, same rounding as ((sg wj) wj) ial
+      if (lane < KU) cf.cbuf[lane] = c;
       __syncwarp();
-      const double wj = (lane < k) ? cf.wrow[j][lane & (KU - 1)] : 0.0;
-      const double c = sg * wj * wj * ial;
-      double incl = c;
-#pragma unroll
-      for (int off = 1; off < KU; off <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += up;
+      double incl;
+      {
+        const double2 *cb = reinterpret_cast<const double2 *>(cf.cbuf);
+        const double2 c01 = cb[0], c23 = cb[1], c45 = cb[2], c67 = cb[3];
+        const int rr = lane & (KU - 1);
+        const double m0 = c01.x, m1 = (rr >= 1) ? c01.y : 0.0, m2 = (rr >= 2) ? c23.x : 0.0, m3 = (rr >= 3) ? c23.y : 0.0;
+        const double m4 = (rr >= 4) ? c45.x : 0.0, m5 = (rr >= 5) ? c45.y : 0.0, m6 = (rr >= 6) ? c67.x : 0.0, m7 = (rr >= 7) ? c67.y : 0.0;
+        incl = ((m0 + m1) + (m2 + m3)) + ((m4 + m5) + (m6 + m7));
       }
       const double dnext = d0 + incl, dprev = d0 + (incl - c);
       if (lane < k && !(dnext > 0.0)) bad = true;
@@ -925,23 +944,28 @@ __device__ __forceinline__ void ud_chain_role(int n, int k, int kpos, double *Wm
       q *= ial;
       const double gam = -sg * wj * q;
       ial = dprev * q;
-      const double dfin = __shfl_sync(0xffffffffu, dnext, k - 1);
-      {   // publish column j (stores predicated by value selection, no branch: lanes < KU write the rank coefficients, lane KU the scalars)
-        const bool rk = lane < KU;
-        double *p0 = rk ? &cf.wj[j][lane] : &cf.winv[j], *p1 = rk ? &cf.gam[j][lane] : &dfin_out[j];
-        const double v0 = rk ? ((lane < k) ? wj : 0.0) : winv, v1 = rk ? ((lane < k) ? gam : 0.0) : dfin;
-        if (lane <= KU) { *p0 = v0; *p1 = v1; }
-      }
+      sgial = sg * ial;
+      // publish column j: lanes < KU the rank coefficients, lane k - 1 (which holds d_k) the new pivot squared
+      if (lane < KU) { cf.wj[j][lane] = (lane < k) ? wj : 0.0; cf.gam[j][lane] = (lane < k) ? gam : 0.0; }
+      if (lane == k - 1) dfin_out[j] = dnext;
       __syncwarp();
       ud_mbar_arrive_lane0(bars + j, lane);   // column j is published: the row owners may apply it
       {
         double t = (rowvalid ? Pn[j * PBL + lane] : 0.0) * winv;
+        const double2 *wj2 = reinterpret_cast<const double2 *>(cf.wj[j]), *gm2 = reinterpret_cast<const double2 *>(cf.gam[j]);
 #pragma unroll
-        for (int r = 0; r < KU; r++) {
-          wl[r] = fma(-cf.wj[j][r], t, wl[r]);
-          t = fma(-cf.gam[j][r], wl[r], t);
+        for (int r2 = 0; r2 < KU / 2; r2++) {
+          const double2 a = wj2[r2], g = gm2[r2];
+          wl[2 * r2] = fma(-a.x, t, wl[2 * r2]);
+          t = fma(-g.x, wl[2 * r2], t);
+          wl[2 * r2 + 1] = fma(-a.y, t, wl[2 * r2 + 1]);
+          t = fma(-g.y, wl[2 * r2 + 1], t);
         }
         if (lane > j && rowvalid) Pn[j * PBL + lane] = t;   // unit-scaled; the write-back multiplies by the new pivot
+        if (lane == j + 1) {   // the next pivot row: leave its W for the next step
+#pragma unroll
+          for (int r = 0; r < KU; r++) cf.wpiv[r] = wl[r];
+        }
       }
       __syncwarp();
     }
