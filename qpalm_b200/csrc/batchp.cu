@@ -21,6 +21,7 @@
 //   factor is current, the factor is UPDATED in place instead (cta_updown_sweep: <= 8 ranks per sweep, entering rows
 //   before leaving rows), exactly where the reference takes cholmod_updown (newton.c:98-108).  All arithmetic is fp64 FMA.
 #include "batch.cuh"
+#include "chol32.cuh"
 #include <math.h>
 #include <string.h>
 
@@ -602,8 +603,11 @@ __device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, 
   for (int j = 0; j < SW; j++) {
     const double pjj = __shfl_sync(0xffffffffu, a[0], j);
     if (!(pjj > 0.0)) bad = true;
-    const double inv = rsqrt(pjj);
-    const double a0 = (lane == j) ? pjj * inv : a[0] * inv;     // lanes < j: upper triangle, never used
+    // branch-free sqrt / reciprocal (chol32.cuh): rsqrt() carries a slow-path CALL, and the values live across that call site were
+    // spilled and reloaded from local memory in every column (five dependent LDL per column under a thrashed 30 KB L1)
+    double ljj, inv;
+    chol32::sqrt_and_rcp(pjj, ljj, inv);
+    const double a0 = (lane == j) ? ljj : a[0] * inv;     // lanes < j: upper triangle, never used
     if (lane == j) rd[c0 + j] = inv;
     if (live && lane >= j && j < wend) Pn[(c0 + j) * LDP + row] = a0;
 #pragma unroll
@@ -876,9 +880,10 @@ __device__ __forceinline__ void ud_flush_block(double *L, int ld, int n, double 
   for (int e = t; e < WIN * UW; e += nthr) {
     const int l = e & (WIN - 1), c = e / WIN;
     if (c < w && k0 + l < n && l >= c) {
-      const double ln = sqrt(dfin[c]);
+      double ln, lninv;
+      chol32::sqrt_and_rcp(dfin[c], ln, lninv);   // branch-free (no slow-path call); every user of the new pivot forms it this way
       L[(size_t)(k0 + l) + (size_t)ld * (k0 + c)] = (l == c) ? ln : Pn[c * PBL + l] * ln;
-      if (l == c) rdiag_g[k0 + c] = 1.0 / ln;
+      if (l == c) rdiag_g[k0 + c] = lninv;
     }
   }
 }
@@ -905,7 +910,11 @@ __device__ __forceinline__ void ud_chain_role(int n, int k, int kpos, double *Wm
     // off the chain: the old pivots are not touched before their own column, so 1 / l_jj and l_jj^2 of all 16 columns are
     // formed up front (lane = column); the new pivots sqrt(d) and the column scaling are left to the write-back
     const double ldiag = (lane < w) ? Pn[lane * PBL + lane] : 1.0;
-    const double winv_l = 1.0 / ldiag, d0_l = ldiag * ldiag;
+    double winv_l;   // 1 / l_jj: reciprocal seed + two Newton steps (the IEEE division subroutine has a slow-path call as well)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(winv_l) : "d"(ldiag));
+    winv_l = fma(winv_l, fma(-ldiag, winv_l, 1.0), winv_l);
+    winv_l = fma(winv_l, fma(-ldiag, winv_l, 1.0), winv_l);
+    const double d0_l = ldiag * ldiag;
     __syncwarp();
     PC(23);
     // Column step.  One dependent chain: pivot row's W (shared memory, left there by that row's lane at the end of the previous
@@ -1031,7 +1040,9 @@ __device__ __forceinline__ void ud_row_role(double *L, int ld, int n, double *rd
             wv[2 * r2 + 1] = fma(-a.y, t, wv[2 * r2 + 1]);
             t = fma(-g.y, wv[2 * r2 + 1], t);
           }
-          Lr[(size_t)ld * c] = t * sqrt(dfin[c]);
+          double ln, lninv;
+          chol32::sqrt_and_rcp(dfin[c], ln, lninv);
+          Lr[(size_t)ld * c] = t * ln;
         }
         // refill the slot just consumed: column c + LVW of this block, or of the next block when this row stays below the window
         const int cn = c + LVW;
