@@ -274,11 +274,55 @@ __device__ __forceinline__ void gemv_rows_body(int nrows, int ncols, int ld, con
     }
   }
 }
+// The same product for an EVEN number of rows <= NT with an even leading dimension (A' yh and Q d: n rows).  A thread owns a PAIR
+// of rows (one 16-byte load per column) and one of G = NT / (nrows / 2) interleaved column groups, so all NT threads have eight
+// 16-byte requests in flight (the one-row-per-thread form had 240 threads x 8 x 8 bytes: the kernel's hottest line, waiting on
+// the L2, profiles/r02g_ncu_source_kbp_solve.txt).  Four accumulators per row, the groups' partial sums are added in group order:
+// fixed summation order, reproducible.  `part` holds G x nrows doubles of shared memory.
+__device__ __forceinline__ void gemv_rowpairs_body(int nrows, int ncols, int ld, const double *__restrict__ M, double *out, double scale,
+                                                   const double *vs, double *part) {
+  const int tid = threadIdx.x, np = nrows >> 1, G = NT / np;
+  const int g = tid / np, p = tid - g * np;
+  if (g < G) {
+    double2 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u] = make_double2(0.0, 0.0);
+    const double *Mp = M + 2 * p;
+    int k0 = g * 8;
+    for (; k0 + 7 < ncols; k0 += G * 8) {
+      double2 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) a[u] = *reinterpret_cast<const double2 *>(Mp + (size_t)(k0 + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double vk = vs[k0 + u];
+        acc[u & 3].x = fma(a[u].x, vk, acc[u & 3].x);
+        acc[u & 3].y = fma(a[u].y, vk, acc[u & 3].y);
+      }
+    }
+    for (int k = k0; k < ncols && k < k0 + 8; k++) {   // this group's ragged last block
+      const double2 a = *reinterpret_cast<const double2 *>(Mp + (size_t)k * ld);
+      const double vk = vs[k];
+      acc[0].x = fma(a.x, vk, acc[0].x);
+      acc[0].y = fma(a.y, vk, acc[0].y);
+    }
+    part[g * nrows + 2 * p] = (acc[3].x + acc[2].x) + (acc[1].x + acc[0].x);
+    part[g * nrows + 2 * p + 1] = (acc[3].y + acc[2].y) + (acc[1].y + acc[0].y);
+  }
+  __syncthreads();
+  for (int i = tid; i < nrows; i += NT) {
+    double t = 0.0;
+    for (int gg = G - 1; gg >= 0; gg--) t += part[gg * nrows + i];
+    out[i] = t * scale;
+  }
+}
 __device__ __forceinline__ void p_gemv_rows(int nrows, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v,
                                             double *out, double scale, const Smem &S) {
   for (int k = threadIdx.x; k < ncols; k += NT) S.vs[k] = v[k];
   __syncthreads();
-  if (nrows <= NT) gemv_rows_body<1, 8>(nrows, ncols, ld, M, out, scale, S.vs);    // one row per thread, 8 columns in flight
+  if (!(nrows & 1) && !(ld & 1) && nrows >= 2 && (nrows >> 1) <= NT)
+    gemv_rowpairs_body(nrows, ncols, ld, M, out, scale, S.vs, S.panel);               // row pairs x column groups (A' yh, Q d)
+  else if (nrows <= NT) gemv_rows_body<1, 8>(nrows, ncols, ld, M, out, scale, S.vs);    // one row per thread, 8 columns in flight
   else gemv_rows_body<4, 4>(nrows, ncols, ld, M, out, scale, S.vs);               // 4 rows x 4 columns in flight
 }
 // out[k] = sum_i M[i + ld*k] v[i], k < ncols (column dots: A d with A' as M); one warp per column
