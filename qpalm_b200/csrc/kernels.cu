@@ -885,6 +885,117 @@ k_ls_select(const unsigned long long *__restrict__ key, const unsigned int *__re
   if (tid == 0) scal[S_TAU] = -carry_b / carry_a;
 }
 
+// ---- 2m <= LS1_MAX: stable LSD radix sort + breakpoint walk in ONE single-CTA launch -----------------------------------
+// The multi-launch sort above costs 24 launches per line search (hist / scan / scatter x 8 passes) whatever the size; for
+// 2m = 4000 (BASELINE config 1) they are 1272 of the 2567 launches of a solve and ~10 ms of its 48 ms.  Here the (key, index)
+// pairs live in shared memory (two ping-pong buffers, 24 bytes per pair), every pass is histogram -> 256-bin exclusive scan ->
+// ordered scatter in rounds of 1024 elements (per-warp digit counts from __match_any_sync, an exclusive scan of each digit's
+// counts over the 32 warps, then one read per element), passes whose digit is the same for all keys are skipped, and the walk
+// of linesearch.c:89-119 (k_ls_select's chunked scan) runs on the sorted pairs without leaving the CTA.  Same stable order
+// (ties by ascending original index) and the same arithmetic in the walk as the multi-launch path: results are bit-identical.
+namespace ls1 {
+constexpr int NT = 1024, NW = NT / 32, LS1_MAX = 8192;
+constexpr size_t smem_bytes(int N) { return (size_t)N * 24 + 2 * 256 * NW + 4 * (256 + 256) + 64; }
+
+__global__ void __launch_bounds__(NT, 1)
+k_sort_select(unsigned long long *key_g, unsigned int *val_g, int N, const double *__restrict__ da, const double *__restrict__ db, double *scal) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(sm_raw), *k1 = k0 + N;
+  unsigned int *v0 = reinterpret_cast<unsigned int *>(k1 + N), *v1 = v0 + N;
+  unsigned int *hist = v1 + N, *running = hist + 256;
+  unsigned short *wcnt = reinterpret_cast<unsigned short *>(running + 256);   // [NW][256]: per-warp digit counts, then their exclusive scan over the warps (< 1024)
+  __shared__ double wa[32], wb[32];
+  __shared__ double carry_a, carry_b;
+  __shared__ int found;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < N; i += NT) { k0[i] = key_g[i]; v0[i] = val_g[i]; }
+  __syncthreads();
+  unsigned long long *kin = k0, *kout = k1;
+  unsigned int *vin = v0, *vout = v1;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = pass * 8;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) atomicAdd(&hist[(unsigned)(kin[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (hist[(unsigned)(kin[0] >> shift) & 255u] == (unsigned)N) { __syncthreads(); continue; }   // one digit for all keys
+    if (warp == 0) {   // exclusive scan of the 256 bins
+      unsigned int loc[8], sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) { loc[t] = hist[lane * 8 + t]; sum += loc[t]; }
+      unsigned int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+      unsigned int run = inc - sum;
+#pragma unroll
+      for (int t = 0; t < 8; t++) { running[lane * 8 + t] = run; run += loc[t]; }
+    }
+    __syncthreads();
+    for (int start = 0; start < N; start += NT) {
+      for (int i = tid; i < NW * 256 / 2; i += NT) reinterpret_cast<unsigned int *>(wcnt)[i] = 0;
+      __syncthreads();
+      const int e = start + tid;
+      const bool valid = e < N;
+      unsigned long long k = 0; unsigned int v = 0; unsigned int dg = 0x10000u + lane;
+      if (valid) { k = kin[e]; v = vin[e]; dg = (unsigned)(k >> shift) & 255u; }
+      const unsigned peers = __match_any_sync(0xffffffffu, dg);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      if (valid && rank == 0) wcnt[warp * 256 + dg] = (unsigned short)__popc(peers);
+      __syncthreads();
+      if (tid < 256) {   // digit tid: exclusive scan of its counts over the warps (in place), then advance the running offset
+        unsigned int acc = 0;
+#pragma unroll 8
+        for (int w = 0; w < NW; w++) { const unsigned int c = wcnt[w * 256 + tid]; wcnt[w * 256 + tid] = (unsigned short)acc; acc += c; }
+        hist[tid] = acc;   // this round's total of the digit (hist is free after the scan)
+      }
+      __syncthreads();
+      if (valid) {
+        const unsigned int pos = running[dg] + wcnt[warp * 256 + dg] + rank;
+        kout[pos] = k; vout[pos] = v;
+      }
+      __syncthreads();
+      if (tid < 256) running[tid] += hist[tid];
+      __syncthreads();
+    }
+    unsigned long long *tk = kin; kin = kout; kout = tk;
+    unsigned int *tv = vin; vin = vout; vout = tv;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += NT) { key_g[i] = kin[i]; val_g[i] = vin[i]; }   // the operator ABI returns the sorted pairs
+  // ---- the walk (k_ls_select on the shared-memory pairs) ----
+  const int nL = (int)scal[S_NL];
+  if (tid == 0) { carry_a = scal[S_ETA] + scal[S_LS_A]; carry_b = scal[S_BETA] - scal[S_LS_B]; found = 0x7fffffff; }
+  __syncthreads();
+  for (int start = 0; start < nL; start += NT) {
+    const int i = start + tid;
+    double ta = 0.0, tb = 0.0, sv = 0.0;
+    if (i < nL) { const unsigned int idx = vin[i]; ta = da[idx]; tb = db[idx]; sv = __longlong_as_double((long long)kin[i]); }
+    double ia = ta, ib = tb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ua; ib += ub; }
+    }
+    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+    __syncthreads();
+    double oa = 0.0, ob = 0.0;
+    for (int w = 0; w < warp; w++) { oa += wa[w]; ob += wb[w]; }
+    double ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+    if (lane == 0) { ea = 0.0; eb = 0.0; }
+    const double a_i = carry_a + (oa + ea), b_i = carry_b + (ob + eb);
+    if (i < nL && (a_i * sv + b_i > 0)) atomicMin(&found, i);
+    __syncthreads();
+    if (found != 0x7fffffff) {
+      if (i == found) scal[S_TAU] = -b_i / a_i;
+      return;
+    }
+    if (tid == NT - 1) { carry_a += oa + ia; carry_b += ob + ib; }
+    __syncthreads();
+  }
+  if (tid == 0) scal[S_TAU] = -carry_b / carry_a;
+}
+}  // namespace ls1
+
 int linesearch_device(Engine *e, int m, const double *Ad, const double *Ax, const double *y, const double *sigma,
                       const double *sqrt_sigma, const double *bmin, const double *bmax) {
   if (m == 0) {
@@ -895,6 +1006,17 @@ int linesearch_device(Engine *e, int m, const double *Ad, const double *Ax, cons
     QB_LAUNCH(k_ls_build, g, kRedThreads, 0, e->stream, m, Ad, Ax, y, sigma, sqrt_sigma, bmin, bmax, e->ls_key[0],
               e->ls_val[0], e->ls_da, e->ls_db, e->partials);
     finalize(e, {S_LS_A, S_LS_B, S_NL}, g);
+    static const bool multi_launch = getenv("QPALM_B200_LS_MULTI") != nullptr;   // A/B and parity runs of the multi-launch path
+    if (2 * m <= ls1::LS1_MAX && !multi_launch) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        QB_CUDA_TRY(cudaFuncSetAttribute(ls1::k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls1::smem_bytes(ls1::LS1_MAX)));
+        attr_set = true;
+      }
+      QB_LAUNCH(ls1::k_sort_select, 1, ls1::NT, ls1::smem_bytes(2 * m), e->stream, e->ls_key[0], e->ls_val[0], 2 * m, e->ls_da, e->ls_db, e->scal_dev);
+      QB_CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
     if (int r = radix_sort_pairs(e, 2 * m)) return r;
   }
   QB_LAUNCH(k_ls_select, 1, 1024, 0, e->stream, e->ls_key[0], e->ls_val[0], e->ls_da, e->ls_db, e->scal_dev);

@@ -99,9 +99,10 @@ def test_residuals_and_active_set_bit_exact(gpu_ops, oracle_ops, n, m, dens, pro
     assert _rel(g["Atyh"], o["Atyh"]) < 1e-13 and _rel(g["dphi"], o["dphi"]) < 1e-13
 
 
-@pytest.mark.parametrize("m", [1, 2, 5, 64, 1000, 2049, 20000])
+@pytest.mark.parametrize("m", [1, 2, 5, 64, 1000, 2049, 4096, 4097, 20000])
 def test_linesearch_ordering_bit_exact(gpu_ops, oracle_ops, m):
-    """exact_linesearch: the sorted breakpoint order (value, then original index) is bit-exact; tau to 1e-10."""
+    """exact_linesearch: the sorted breakpoint order (value, then original index) is bit-exact; tau to 1e-10.
+    2m <= 8192 takes the single-CTA sort + walk (m = 4096 is its largest size), larger m the multi-launch radix sort."""
     rng = np.random.default_rng(m)
     Ad = rng.standard_normal(m)
     Ad[rng.random(m) < 0.1] = 0.0                 # delta = +-0: infinite / NaN breakpoints
