@@ -576,17 +576,17 @@ __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, cons
           }
           base[a][e][h] = bv;
         }
+    // fragment addresses once per tile; the callers zero the panel columns [w, wpad), so the product loop has no predicate and no
+    // branch (the first version selected `c < w ? load : 0` per fragment: ~60 integer / branch instructions per four DMMAs)
+    const double *pa0 = U + fk * LDP - u0 + ra[0], *pa1 = U + fk * LDP - u0 + ra[1];
+    const double *pb0 = U + fk * LDP - u0 + rb[0], *pb1 = U + fk * LDP - u0 + rb[1];
+#pragma unroll 3
     for (int kc = 0; kc < wpad; kc += 4) {
-      const int c = kc + fk;
-      const bool live = c < w;
-      const double *Uc = U + (live ? c : 0) * LDP - u0;
-      double fa[2], fb[2];
-#pragma unroll
-      for (int t = 0; t < 2; t++) { fa[t] = live ? Uc[ra[t]] : 0.0; fb[t] = live ? Uc[rb[t]] : 0.0; }
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) bp_dmma884(acc[a][e][0], acc[a][e][1], fa[a], fb[e]);
+      const double fa0 = pa0[kc * LDP], fa1 = pa1[kc * LDP], fb0 = pb0[kc * LDP], fb1 = pb1[kc * LDP];
+      bp_dmma884(acc[0][0][0], acc[0][0][1], fa0, fb0);
+      bp_dmma884(acc[0][1][0], acc[0][1][1], fa0, fb1);
+      bp_dmma884(acc[1][0][0], acc[1][0][1], fa1, fb0);
+      bp_dmma884(acc[1][1][0], acc[1][1][1], fa1, fb1);
     }
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -778,6 +778,10 @@ __device__ __forceinline__ void cta_potrf(double *L, int ld, const double *src, 
       panel_forward(Pn, S.v, S.rd, k0, w, rows);   // ends with a barrier; only reads the panel
     }
     PQ(20);
+    if (w & 3) {   // ragged last panel: zero the pad columns the DMMA product loop reads (no trailing matrix then, but keep it defined)
+      for (int idx = tid; idx < (((w + 3) & ~3) - w) * rows; idx += NT) { const int t = w + idx / rows, r = idx - (t - w) * rows; Pn[t * LDP + r] = 0.0; }
+      __syncthreads();
+    }
     cta_rank_update_lower(L, ld, src, lds, sscale, beta, first, k0 + w, n, Pn, k0, w, -1.0);
     __syncthreads();
     PQ(21);
@@ -833,9 +837,20 @@ __device__ __forceinline__ void cta_syrk_list(double *dst, int ld, int n, const 
   const int tid = threadIdx.x;
   for (int off = 0; off < cnt; off += PW) {
     const int w = (cnt - off < PW) ? cnt - off : PW;
-    for (int idx = tid; idx < w * n; idx += NT) {
-      const int c = idx / n, i = idx - c * n;
-      S.panel[c * LDP + i] = wgt[off + c] * At[(size_t)i + (size_t)n * list[off + c]];
+    const int wpad = (w + 3) & ~3;   // the DMMA product loop walks 4 columns at a time: zero the pad columns
+    // gather: thread = row, eight columns (list entries) requested before any is stored -- the one-element-at-a-time form chained
+    // list[c] -> A'[:, list[c]] loads behind an integer division per element
+    for (int i = tid; i < n; i += NT) {
+      for (int c0 = 0; c0 < wpad; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int c = c0 + u;
+          v[u] = (c < w) ? wgt[off + c] * At[(size_t)i + (size_t)n * list[off + c]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (c0 + u < wpad) S.panel[(c0 + u) * LDP + i] = v[u];
+      }
     }
     __syncthreads();
     cta_rank_update_lower(dst, ld, nullptr, 0, 0.0, 0.0, false, 0, n, S.panel, 0, w, sign);
@@ -1589,9 +1604,14 @@ __global__ void __launch_bounds__(NT, QB_BP_MINB) kbp_solve(const Args P) {
         if (refac) {
           const BCtl c = P.ctl[b];
           if (c.scratch) {
-            for (int idx = tid; idx < n * n; idx += NT) {
-              const int j = idx / n, i = idx - j * n;
-              if (i >= j) Hb[(size_t)i + (size_t)ld * j] = P.Qs[(size_t)i + (size_t)n * j] * c.c;
+            for (int i = tid; i < n; i += NT) {   // H <- c Q (lower): thread = row, eight columns in flight
+              for (int j0 = 0; j0 <= i; j0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = (j0 + u <= i) ? P.Qs[(size_t)i + (size_t)n * (j0 + u)] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (j0 + u <= i) Hb[(size_t)i + (size_t)ld * (j0 + u)] = v[u] * c.c;
+              }
             }
             __syncthreads();
           }
