@@ -59,15 +59,22 @@ class Batch:
     def ok(self):
         return bool(self.h)
 
-    def solve(self, q, bmin, bmax):
+    def solve(self, q, bmin, bmax, x=None, y=None, info=None, raw_info=False):
+        """One call of the batch entry point with HOST buffers (H2D of q / bmin / bmax, solve, D2H of x / y / info).
+        x, y, info: optional caller-owned result buffers (e.g. pinned memory) reused across calls; raw_info=True returns the
+        QPALMInfo array itself instead of a list of dicts."""
         nb = q.shape[0]
         q, bmin, bmax = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, bmin, bmax))
-        x, y = np.zeros((nb, self.n)), np.zeros((nb, self.m))
-        info = (QPALMInfo * nb)()
+        if x is None:
+            x = np.zeros((nb, self.n))
+        if y is None:
+            y = np.zeros((nb, self.m))
+        if info is None:
+            info = (QPALMInfo * nb)()
         rc = self.lib.qpalm_b200_batch_solve(self.h, nb, fptr(q), fptr(bmin), fptr(bmax), fptr(x), fptr(y), info)
         if rc:
             raise RuntimeError(f"qpalm_b200_batch_solve failed: {rc}")
-        return x, y, _infos(info, nb)
+        return x, y, (info if raw_info else _infos(info, nb))
 
     def upload(self, q, bmin, bmax):
         self._res = tuple(np.ascontiguousarray(a, dtype=np.float64) for a in (q, bmin, bmax))

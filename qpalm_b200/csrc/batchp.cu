@@ -623,7 +623,12 @@ __device__ __forceinline__ void panel_load_async(double *Pn, const double *L, in
 
 // The PW = 32 column panel is factorised as two 16-column sub-panels so that every per-thread register array is 16
 // doubles (a 32-wide version needs 64 registers per array and spills at 3 CTAs / SM).
-constexpr int SW = 16;
+#ifndef QB_BP_SW
+#define QB_BP_SW 16
+#endif
+constexpr int SW = QB_BP_SW;          // sub-panel width of the in-CTA Cholesky (the diagonal block one warp factors in registers)
+static_assert(PW % SW == 0 || PW == 24, "panel = whole sub-panels (24 = 16 + 8 in the 16-wide build)");
+constexpr int UPW = PW - SW;          // columns of the panel to the right of a sub-panel (at most)
 
 // Cholesky of the 16 x 16 block at (c0, c0) of the panel (P[t][r], t = column, r = row), warp 0; lane = row, the row
 // lives in registers.  The column loop is ROLLED around a rotating register file: a[0] is always the current column and
@@ -633,7 +638,7 @@ constexpr int SW = 16;
 // of this large kernel it ran at instruction-fetch-miss speed: 27 us per block in situ, phase profile of round 1.)  The
 // arithmetic and its order are those of the unrolled form, so results are bit-identical to it.
 // Columns/rows >= w (ragged last panel) are skipped.  rd[c0 + j] = 1 / l_jj.
-__device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, int w, int *info) {
+__device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, double *colbuf, int c0, int w, int *info) {
   const int lane = threadIdx.x & 31;
   const int row = c0 + lane;
   const int wend = (w - c0 < SW) ? w - c0 : SW;
@@ -654,9 +659,15 @@ __device__ __noinline__ void warp_factor_diag16(double *Pn, double *rd, int c0, 
     const double a0 = (lane == j) ? ljj : a[0] * inv;     // lanes < j: upper triangle, never used
     if (lane == j) rd[c0 + j] = inv;
     if (live && lane >= j && j < wend) Pn[(c0 + j) * LDP + row] = a0;
+    // column j is broadcast through shared memory (two alternating 32-entry buffers, one __syncwarp per column): the 15 loads are
+    // independent and issue back to back, where 15 64-bit shuffles each exposed their latency before the FMA that consumes them
+    // (the loop ran at ~1270 clocks per column on an otherwise idle SM)
+    double *cb = colbuf + ((j & 1) << 5);
+    cb[lane] = a0;
+    __syncwarp();
 #pragma unroll
     for (int c = 1; c < SW; c++) {
-      const double lcj = __shfl_sync(0xffffffffu, a0, (j + c) & 31);
+      const double lcj = cb[(j + c) & 31];
       a[c - 1] = (lane >= j + c) ? fma(-a0, lcj, a[c]) : a[c];   // column j + c moves to register c - 1
     }
     a[SW - 1] = 0.0;
@@ -685,20 +696,21 @@ __device__ __forceinline__ void panel_solve16(double *Pn, const double *rd, int 
   }
 }
 
-// rows r >= 16: P[16 + c][r] -= sum_{t < 16} P[t][r] P[t][16 + c]  for 16 + c <= min(r, w - 1)
-__device__ __forceinline__ void panel_update16(double *Pn, int w, int rows) {
-  for (int r = SW + threadIdx.x; r < rows; r += NT) {
-    double acc[SW];
+// after sub-panel [c0, c0 + SW): the panel's columns to its right, rows r >= c0 + SW:
+//   P[c0 + SW + c][r] -= sum_{t < SW} P[c0 + t][r] P[c0 + t][c0 + SW + c]   for c0 + SW + c <= min(r, w - 1)
+__device__ __forceinline__ void panel_update16(double *Pn, int c0, int w, int rows) {
+  for (int r = c0 + SW + threadIdx.x; r < rows; r += NT) {
+    double acc[UPW];
 #pragma unroll
-    for (int c = 0; c < SW; c++) acc[c] = 0.0;
+    for (int c = 0; c < UPW; c++) acc[c] = 0.0;
 #pragma unroll 4
     for (int t = 0; t < SW; t++) {
-      const double lr = Pn[t * LDP + r];
+      const double lr = Pn[(c0 + t) * LDP + r];
 #pragma unroll
-      for (int c = 0; c < SW; c++) acc[c] = fma(lr, Pn[t * LDP + SW + c], acc[c]);
+      for (int c = 0; c < UPW; c++) if (c0 + SW + c < PW) acc[c] = fma(lr, Pn[(c0 + t) * LDP + c0 + SW + c], acc[c]);
     }
 #pragma unroll
-    for (int c = 0; c < SW; c++) if (SW + c < w && SW + c <= r) Pn[(SW + c) * LDP + r] -= acc[c];
+    for (int c = 0; c < UPW; c++) if (c0 + SW + c < w && c0 + SW + c <= r) Pn[(c0 + SW + c) * LDP + r] -= acc[c];
   }
 }
 
@@ -752,22 +764,18 @@ __device__ __forceinline__ void cta_potrf(double *L, int ld, const double *src, 
     } else panel_load_async(Pn, L, ld, k0, w, rows);
     __syncthreads();
     PQ(16);
-    if (tid < 32) warp_factor_diag16(Pn, S.rd, 0, w, info);
-    __syncthreads();
-    PQ(17);
-    panel_solve16(Pn, S.rd, 0, w, rows);
-    __syncthreads();
-    PQ(18);
-    if (w > SW) {
-      panel_update16(Pn, w, rows);
-      __syncthreads();
-      PQ(19);
-      if (tid < 32) warp_factor_diag16(Pn, S.rd, SW, w, info);
+    for (int c0 = 0; c0 < w; c0 += SW) {   // sub-panels: diagonal block (one warp) -> rows below -> the panel's columns to the right
+      if (tid < 32) warp_factor_diag16(Pn, S.rd, S.vs, c0, w, info);
       __syncthreads();
       PQ(17);
-      panel_solve16(Pn, S.rd, SW, w, rows);
+      panel_solve16(Pn, S.rd, c0, w, rows);
       __syncthreads();
       PQ(18);
+      if (c0 + SW < w) {
+        panel_update16(Pn, c0, w, rows);
+        __syncthreads();
+        PQ(19);
+      }
     }
     for (int idx = tid; idx < w * rows; idx += NT) {   // final columns of L
       const int t = idx / rows, r = idx - t * rows;

@@ -15,7 +15,7 @@ for f in dense updown_flow kernels api ops compat kkt batch batchp prof shard sp
 done
 # the persistent batch engine a second time in its 4-CTAs-per-SM shape (see the header of batchp.cu)
 if [ ! -f build/batchp4.o ] || [ batchp.cu -nt build/batchp4.o ] || [ batch.cuh -nt build/batchp4.o ] || [ common.cuh -nt build/batchp4.o ] || [ engine.cuh -nt build/batchp4.o ]; then
-  $NVCC $FLAGS -DQB_BP_VARIANT4 -c batchp.cu -o build/batchp4.o &
+  $NVCC $FLAGS -DQB_BP_VARIANT4 ${QB_BP4_FLAGS:--DQB_BP_SW=8} -c batchp.cu -o build/batchp4.o &
   pids+=($!)
 fi
 for p in "${pids[@]}"; do wait $p; done
