@@ -323,7 +323,11 @@ __device__ __forceinline__ void p_gemv_rows(int nrows, int ncols, int ld, const 
   if (!(nrows & 1) && !(ld & 1) && nrows >= 2 && (nrows >> 1) <= NT)
     gemv_rowpairs_body(nrows, ncols, ld, M, out, scale, S.vs, S.panel);               // row pairs x column groups (A' yh, Q d)
   else if (nrows <= NT) gemv_rows_body<1, 8>(nrows, ncols, ld, M, out, scale, S.vs);    // one row per thread, 8 columns in flight
+#ifdef QB_BP_VARIANT4
+  else gemv_rows_body<4, 2>(nrows, ncols, ld, M, out, scale, S.vs);               // 64 registers: 4 x 4 accumulators + 16 loads in flight spill in the loop
+#else
   else gemv_rows_body<4, 4>(nrows, ncols, ld, M, out, scale, S.vs);               // 4 rows x 4 columns in flight
+#endif
 }
 // out[k] = sum_i M[i + ld*k] v[i], k < ncols (column dots: A d with A' as M); one warp per column
 __device__ __forceinline__ void p_gemv_cols(int len, int ncols, int ld, const double *__restrict__ M, const double *__restrict__ v, double *out,
@@ -578,11 +582,18 @@ __device__ __forceinline__ void cta_rank_update_lower(double *dst, int ldd, cons
         }
     // fragment addresses once per tile; the callers zero the panel columns [w, wpad), so the product loop has no predicate and no
     // branch (the first version selected `c < w ? load : 0` per fragment: ~60 integer / branch instructions per four DMMAs)
-    const double *pa0 = U + fk * LDP - u0 + ra[0], *pa1 = U + fk * LDP - u0 + ra[1];
-    const double *pb0 = U + fk * LDP - u0 + rb[0], *pb1 = U + fk * LDP - u0 + rb[1];
+    // 32-bit shared-window addresses (four registers instead of four 64-bit generic pointers: at 64 registers per thread the
+    // pointers were spilled inside this loop)
+    const unsigned ub = (unsigned)__cvta_generic_to_shared(U + fk * LDP - u0);
+    const unsigned sa0 = ub + 8u * (unsigned)ra[0], sa1 = ub + 8u * (unsigned)ra[1], sb0 = ub + 8u * (unsigned)rb[0], sb1 = ub + 8u * (unsigned)rb[1];
 #pragma unroll 3
     for (int kc = 0; kc < wpad; kc += 4) {
-      const double fa0 = pa0[kc * LDP], fa1 = pa1[kc * LDP], fb0 = pb0[kc * LDP], fb1 = pb1[kc * LDP];
+      const unsigned o = (unsigned)(kc * LDP * 8);
+      double fa0, fa1, fb0, fb1;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fa0) : "r"(sa0 + o));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fa1) : "r"(sa1 + o));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fb0) : "r"(sb0 + o));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fb1) : "r"(sb1 + o));
       bp_dmma884(acc[0][0][0], acc[0][0][1], fa0, fb0);
       bp_dmma884(acc[0][1][0], acc[0][1][1], fa0, fb1);
       bp_dmma884(acc[1][0][0], acc[1][0][1], fa1, fb0);
