@@ -72,3 +72,26 @@ def test_batch_is_deterministic():
     x2, y2, i2 = qb.solve_batch(b)
     assert np.array_equal(x1, x2) and np.array_equal(y1, y2)
     assert [i["iter"] for i in i1] == [i["iter"] for i in i2]
+
+
+@pytest.mark.parametrize("cap", ["0", "8", "1000000"], ids=["refactorize_always", "one_sweep", "sweeps_always"])
+def test_batch_update_and_refactorization_paths_agree(cap, monkeypatch, engine):
+    """Same matrix either way: the persistent engine's in-CTA update sweeps (chain warp + row owners) against its incremental
+    SYRK + refactorization, selected through the rank cap (default 40).  Every instance must land on the oracle's solution
+    and iteration count whichever path its Newton systems took, and the sweep path must actually have run."""
+    if engine != "persistent":
+        pytest.skip("the lock-step engine always refactorizes")
+    monkeypatch.setenv("QPALM_B200_BATCH_UPDOWN_MAX_RANK", cap)
+    b = problems.mpc_batch(5, n=61, m0=90, seed=21)      # 61 columns: three full 16-column blocks + a ragged one, rows beyond the 32-row window
+    h = qb.Batch(b.Q, b.A, b.settings, 5)
+    xs, ys, infos = h.solve(b.q, b.bmin, b.bmax)
+    st = h.stats(5)
+    h.cleanup()
+    assert (st["updown_sweeps"] > 0) == (cap != "0"), st
+    assert st["updown_failed"] == 0
+    for k in range(5):
+        q = b.instance(k)
+        o = solve_qp("oracle", q.Q.copy(), q.A.copy(), q.q, q.bmin, q.bmax, **q.settings)
+        assert infos[k]["status_val"] == o.status_val == 1
+        assert abs(infos[k]["iter"] - o.iter) <= max(1, int(np.ceil(0.05 * o.iter))), (k, infos[k]["iter"], o.iter)
+        assert _rel(xs[k], o.x) < 1e-7 and _rel(ys[k], o.y) < 1e-7
