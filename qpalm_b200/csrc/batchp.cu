@@ -7,19 +7,23 @@
 // line search) with block-level barriers between the steps, and take the next instance when done.  There is no host
 // synchronisation inside a solve and no instance waits for another.
 //
-// Memory plan (B200): the shared A' (n x m) and D Q D (n x n) are read by every CTA and stay in the 126 MB L2; the
-// per-instance H / L (n x n lower, column-major) and vectors are touched by one CTA only and are L2-resident while
-// the instance is in flight (3 CTAs per SM x 148 SMs in flight).  Shared memory per CTA (~70 KB, 3 CTAs / SM) holds
-// one 32-column panel of the factor (Cholesky, triangular solves, rank-32 SYRK chunks), the radix-sort buffers of the
-// line search (2m <= 2048 keys) and the staged GEMV operand.
+// Memory plan (B200): the shared A' (n x m), A (m x n) and D Q D (n x n) are read by every CTA and stay in the 126 MB L2; the
+// per-instance H / L (n x n lower, column-major) and vectors are touched by one CTA only.  At 512 instances the factors
+// (2 x 230 KB each) do not fit the L2 and stream from HBM, which is why every pass over them is written as a batch of
+// requests (cp.async, eight loads in flight, rows requested one block ahead) rather than load -> use.  Shared memory per CTA
+// (72 KB at 3 CTAs / SM, 55 KB at 4) holds one panel of the factor (Cholesky, triangular solves, SYRK chunks) -- or, during an
+// update sweep, the rows of W, the chain warp's ring of window blocks and the row owners' staging ring --, the radix-sort
+// buffers of the line search (2m <= 2048 keys) and the staged GEMV operand.
 //
 // The Newton system (Q + A_J' Sigma_J A_J + I/gamma) d = -dphi  (src/newton.c:96-118, solver_interface.c:319-519):
-//   H is kept per instance and updated incrementally (+ entering / - leaving / +- sigma changes) by an in-CTA
-//   rank-32-chunk SYRK, L <- chol(H + beta I) by an in-CTA right-looking blocked Cholesky (32-column panels: diagonal
-//   block in one warp's registers, panel solve one row per thread, 4 x 4 register-blocked trailing update), then two
-//   blocked triangular solves.  When the active set changes by at most min(0.1 (n + m), max_rank_update) rows and the
-//   factor is current, the factor is UPDATED in place instead (cta_updown_sweep: <= 8 ranks per sweep, entering rows
-//   before leaving rows), exactly where the reference takes cholmod_updown (newton.c:98-108).  All arithmetic is fp64 FMA.
+//   H is kept per instance and updated incrementally (+ entering / - leaving / +- sigma changes) by an in-CTA SYRK in chunks of
+//   one panel width, L <- chol(H + beta I) by an in-CTA right-looking blocked Cholesky (diagonal sub-blocks in one warp's
+//   registers, panel solve one row per thread); SYRK and trailing updates run on the FP64 tensor pipe (mma.sync m8n8k4, 16 x 16
+//   tiles per warp); then two blocked triangular solves.  When the active set changes by at most min(0.1 (n + m),
+//   max_rank_update) rows -- and at most 40, see p_control -- and the factor is current, the factor is UPDATED in place instead
+//   (cta_updown_sweep: <= 8 ranks per sweep, entering rows before leaving rows; a chain warp on the diagonal, every other thread
+//   the owner of one row, per-column mbarriers), where the reference takes cholmod_updown (newton.c:98-108).  All arithmetic is
+//   fp64 FMA / DMMA.
 #include "batch.cuh"
 #include "chol32.cuh"
 #include <math.h>
@@ -28,17 +32,18 @@
 using namespace qb;
 
 // Build-time shape of a CTA; this file is compiled twice (build.sh):
-//   default            8 warps, 32-column panel, both sort buffers in shared memory: 80 registers x 256 threads, 72 KB
-//                      -> 3 CTAs / SM (444 slots on a B200).  Best per-wave throughput (444 instances in 93 ms).
-//   -DQB_BP_VARIANT4   8 warps, 24-column panel (sub-panels 16 + 8), one sort buffer in shared memory and the other in the
-//                      instance's global arrays, registers capped at 64: 55 KB -> 4 CTAs / SM (592 slots).  Slower per
-//                      wave (592 instances in 130 ms) but the BASELINE sweep of 512 instances per GPU fits in ONE wave:
-//                      127 ms instead of 139 ms with the 68-instance tail of the default shape.  batch.cu picks it when
-//                      3 * SMs < nb <= 4 * SMs.
+//   default            8 warps, 32-column panel (16-wide sub-panels), both sort buffers in shared memory: 80 registers x 256
+//                      threads, 72 KB -> 3 CTAs / SM (444 slots on a B200).  Best per-wave throughput: 444 instances in
+//                      57.9 ms (7675 solves/s), 4096 instances in 488 ms (8396 solves/s) at the end of round 2.
+//   -DQB_BP_VARIANT4   8 warps, 24-column panel (-DQB_BP_SW=8: 8-wide sub-panels), one sort buffer in shared memory and the other
+//                      in the instance's global arrays, registers capped at 64: 55 KB -> 4 CTAs / SM (592 slots).  Slower per
+//                      instance (64 registers: several loops are shaped around that, see QB_BP_SW and p_gemv_rows) but the
+//                      BASELINE sweep of 512 instances per GPU fits in ONE wave: 78.8 ms against 90.3 ms with the 68-instance
+//                      tail of the default shape.  batch.cu picks it when 3 * SMs < nb <= 4 * SMs.
 // Other shapes measured in round 1 (512 instances): 192 threads / PW 24 / 4 per SM 138.6 ms; 192 / PW 16 / 4 per SM
 // 147.7 ms; 256 / PW 16 / 64 regs / 4 per SM 133.0 ms; 192 threads / PW 32 / 3 per SM 192.5 ms (fewer threads per CTA
 // cost more than the extra occupancy buys); 4-per-SM shape with 224 threads (72 registers) 142.8 ms, with 288 threads
-// (56 registers) 145.9 ms.
+// (56 registers) 145.9 ms.  (The update sweep of round 2 maps thread t to row t of L: NT >= n.)
 #ifdef QB_BP_VARIANT4
 #define QB_BP_NAMESPACE bp4
 #define QB_BP_SUPPORTED batchp4_supported
@@ -72,6 +77,7 @@ constexpr int NT = QB_BP_NT, NW = NT / 32;
 constexpr int PW = QB_BP_PW;      // panel width (sub-panels of 16 + 8 columns)
 constexpr int NMAX = 240;         // largest n of this engine (panel = PW x LDP doubles of shared memory)
 constexpr int LDP = NMAX + 1;     // odd leading dimension: conflict-free row and column access
+static_assert(NMAX <= NT, "the update sweep maps thread t to row t of the factor");
 constexpr int SORT_MAX = 2048;    // largest 2m
 constexpr int VS_LEN = (QB_BP_PW == 32) ? 1024 : 960;   // staged GEMV operand (max(n, m) doubles)
 constexpr size_t kSortBytes = (size_t)SORT_MAX * (QB_BP_SORT_GLOBAL ? 1 : 2) * (8 + 4) + sizeof(unsigned) * (NW * 256 + 256 + 256);
