@@ -31,11 +31,20 @@ def test_mat_vec_trio(gpu_ops, oracle_ops, n, m, dens):
     assert _rel(gpu_ops.mat_vec(p.Q, x), oracle_ops.mat_vec(p.Q, x)) < 1e-13
 
 
-def test_mat_vec_reference_vectors(gpu_ops):
-    """Known answers of tests/src/test_solver_interface.c:106-127."""
-    A = CSC(3, 2, [0, 3, 6], [0, 1, 2, 0, 1, 2], [1.0, 3.0, 5.0, 2.0, 4.0, 4.5])  # placeholder dense 3x2
-    x = np.array([1.0, -0.5])
-    np.testing.assert_allclose(gpu_ops.mat_vec(A, x), A.to_scipy() @ x, rtol=1e-14)
+def test_solver_interface_known_answers_on_the_gpu(gpu_ops):
+    """Known answers of the reference's own tests/src/test_solver_interface.c:106-159 (the 3 x 2 A, the 2 x 2 Q with both
+    triangles stored): mat_vec, mat_tpose_vec, mat_inf_norm_cols / rows, ldlchol + ldlsolveLD_neg_dphi with and without
+    the proximal term -- through the CUDA operator ABI (test_oracle.py runs the same vectors through the oracle)."""
+    f = problems.solver_interface_fixture()
+    np.testing.assert_allclose(gpu_ops.mat_vec(f["A"], f["Qd"]), f["A_Qd"], atol=1e-8)
+    np.testing.assert_allclose(gpu_ops.mat_vec(f["Q"], f["Qd"]), f["Q_Qd"], atol=1e-8)
+    np.testing.assert_allclose(gpu_ops.mat_tpose_vec(f["A"], f["Ad"]), f["At_Ad"], atol=1e-8)
+    np.testing.assert_allclose(gpu_ops.norm_cols(f["A"]), f["col_norms"], atol=1e-8)
+    np.testing.assert_allclose(gpu_ops.norm_rows(f["A"]), f["row_norms"], atol=1e-8)
+    d, _ = gpu_ops.newton_solve(f["Q"], None, None, None, 0.0, -f["neg_rhs"], want_L=False)
+    np.testing.assert_allclose(d, f["d_noprox"], atol=1e-8)
+    d, _ = gpu_ops.newton_solve(f["Q"], None, None, None, 1.0 / f["gamma"], -f["neg_rhs"], want_L=False)
+    np.testing.assert_allclose(d, f["d_prox"], atol=1e-8)
 
 
 def test_q_upper_triangle_ignored(gpu_ops, oracle_ops):
