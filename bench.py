@@ -268,7 +268,8 @@ def bench_dense(args, lib, steps, warmup, sample_clocks=True):
         sigma_update_calls=int(st1.sigma_update_calls - st0.sigma_update_calls) // steps, alg_bytes=(st1.algorithmic_bytes - st0.algorithmic_bytes) / steps,
         clocks=clocks, h2d=h2d, d2h=d2h, x=res.x, y=res.y, objective=res.objective)
     s.cleanup()
-    # e2e: setup (H2D + Ruiz) + solve + solution read-back through the public API, host buffers
+    # e2e: setup (H2D + Ruiz) + solve + solution read-back through the public API, host buffers (pageable, as the caller's CSC
+    # arrays are; pinning the 1.28 GB of matrix values made qpalm_setup slower on the box: 0.63 s against 0.21 s)
     e2e, setup_warm = [], []
     for _ in range(max(1, min(steps, 2))):
         t0 = time.perf_counter()
