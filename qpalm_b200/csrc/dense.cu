@@ -881,11 +881,11 @@ __global__ void __launch_bounds__(NT) k_bwd_step(const double *__restrict__ L, i
 // ================================================================================================
 // Dataflow triangular solves (single matrix): ONE cooperative launch for forward + backward substitution.
 // CTA c owns the 128-row blocks c, c + G, ... : forward it accumulates  t_i = b_i - sum_{j<i} L_ij y_j  tile by tile,
-// consuming y_j as soon as its owner has published it (release/acquire flag in global memory), then forms
+// consuming y_j as soon as its owner has published it (tagged 16-byte packets in global memory, see pk_store), then forms
 // y_i = inv(L_ii) t_i and publishes it; backward likewise over the block columns in descending order.  The tile of the
-// next step is loaded into registers BEFORE the CTA waits for the flag, so the critical path per block is one L2 round
-// trip + two 128 x 128 matrix-vector products from registers / shared memory (about 2 us), instead of one kernel launch
-// per block (about 22 us).  The cooperative launch guarantees that all CTAs are co-resident, which the spin-waits need.
+// next step is loaded into registers BEFORE the CTA waits for the packets, so the critical path per block is one L2 round
+// trip + two 128 x 128 matrix-vector products from registers / shared memory (measured 3.7 us per block step at n = 8000),
+// instead of one kernel launch per block (about 22 us).  The cooperative launch guarantees that all CTAs are co-resident, which the spin-waits need.
 // ================================================================================================
 namespace flow {
 constexpr int NB = 128, NT = 256;
@@ -909,6 +909,23 @@ __device__ __forceinline__ void publish(int *f, int epoch) {
   __syncthreads();
   if (threadIdx.x == 0) { __threadfence(); st_release(f, epoch); }
 }
+// Solution blocks travel between CTAs as TAGGED PACKETS: one 16-byte store {lo32, epoch, hi32, epoch} per double, the reader
+// spins on its own packet until both tags carry the launch's epoch (tear-proof at 8-byte granularity -- the layout of NCCL's LL
+// protocol).  Value and "it is there" arrive in ONE L2 round trip and the producer needs neither __threadfence() nor a separate
+// flag store; the first version (fence -> flag -> acquire poll -> dependent load of the values) paid three on the chain of every
+// block.  Measured effect: 66 -> 60 us per solve at n = 1000, 477 -> 469 us at n = 8000 (the step is bound elsewhere there).  Epoch-stamped, so nothing is cleared between launches.
+__device__ __forceinline__ void pk_store(uint4 *pk, double v, int epoch) {
+  const long long b = __double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(pk), "r"((unsigned)(b & 0xffffffffll)), "r"((unsigned)epoch),
+               "r"((unsigned)((unsigned long long)b >> 32)) : "memory");
+}
+__device__ __forceinline__ double pk_wait(const uint4 *pk, int epoch) {
+  unsigned lo, t0, hi, t1;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(pk) : "memory");
+  } while (t0 != (unsigned)epoch || t1 != (unsigned)epoch);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
 __device__ __forceinline__ void load_block_to_smem(double *Xs, const double *Xg) {
   const double2 *src = reinterpret_cast<const double2 *>(Xg);
   double2 *dst = reinterpret_cast<double2 *>(Xs);
@@ -917,13 +934,13 @@ __device__ __forceinline__ void load_block_to_smem(double *Xs, const double *Xg)
 }
 
 __global__ void __launch_bounds__(NT, 1)
-k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X, double *v, int nblk, int *flags, int epoch) {
+k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X, double *v, int nblk, uint4 *packets, int epoch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *Xs = reinterpret_cast<double *>(smem_raw);   // inverse of the current diagonal block, column-major
   double *xs = Xs + NB * NB;                           // incoming solution block
   double *scratch = xs + NB;                           // 2 * NB partial sums
   double *rs = scratch + 2 * NB;                       // right-hand side of the diagonal solve
-  int *flag_f = flags, *flag_b = flags + nblk;
+  uint4 *pk_f = packets, *pk_b = packets + (size_t)nblk * NB;   // forward (y) and backward (x) blocks
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid & (NB - 1), h = tid >> 7;
   const int G = gridDim.x;
 
@@ -936,8 +953,8 @@ k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X,
       double t[64];
 #pragma unroll
       for (int c = 0; c < 64; c++) t[c] = Lp[(size_t)c * ld];        // in flight while waiting for y_j
-      wait_flag(flag_f + j, epoch);
-      if (tid < NB) xs[tid] = __ldcg(v + (size_t)j * NB + tid);
+      __syncthreads();   // the previous step's readers of xs are done
+      if (tid < NB) xs[tid] = pk_wait(pk_f + (size_t)j * NB + tid, epoch);
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < 64; c += 4) {
@@ -963,9 +980,13 @@ k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X,
       }
       scratch[h * NB + r] = (b0 + b1) + (b2 + b3);
       __syncthreads();
-      if (h == 0) v[(size_t)i * NB + r] = scratch[r] + scratch[NB + r];
+      if (h == 0) {
+        const double yv = scratch[r] + scratch[NB + r];
+        v[(size_t)i * NB + r] = yv;                       // for this CTA's own backward step
+        pk_store(pk_f + (size_t)i * NB + r, yv, epoch);    // for the CTAs below
+      }
     }
-    publish(flag_f + i, epoch);
+    __syncthreads();   // scratch / rs / Xs are reused by the next block of this CTA
   }
 
   // ---------------- backward: L' x = y ----------------
@@ -983,8 +1004,8 @@ k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X,
       for (int u = 0; u < 16; u++)
 #pragma unroll
         for (int q = 0; q < 4; q++) t[u][q] = Lp[(size_t)u * ld + 32 * q];
-      wait_flag(flag_b + i, epoch);
-      if (tid < NB) xs[tid] = __ldcg(v + (size_t)i * NB + tid);
+      __syncthreads();   // the previous step's readers of xs are done
+      if (tid < NB) xs[tid] = pk_wait(pk_b + (size_t)i * NB + tid, epoch);
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < 4; q++) {
@@ -993,8 +1014,7 @@ k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X,
         for (int u = 0; u < 16; u++) acc[u] = fma(t[u][q], dv, acc[u]);
       }
     }
-    // the forward value y_j was published (fenced) by this CTA; every consumer of it finished before x_{j+1} appeared
-    if (j == nblk - 1) wait_flag(flag_f + j, epoch);   // uniform: makes the smem reuse below safe in the degenerate case
+    // y_j was written to v by THIS CTA in its forward pass (CTA barriers since then order it for every thread here)
 #pragma unroll
     for (int u = 0; u < 16; u++) {
       const double sacc = warp_sum(acc[u]);
@@ -1007,13 +1027,12 @@ k_solve_flow(const double *__restrict__ L, int ld, const double *__restrict__ X,
 #pragma unroll
       for (int q = 0; q < 4; q++) a = fma(Xs[lane + 32 * q + NB * c], rs[lane + 32 * q], a);
       a = warp_sum(a);
-      if (lane == 0) v[(size_t)j * NB + c] = a;
+      if (lane == 0) { v[(size_t)j * NB + c] = a; pk_store(pk_b + (size_t)j * NB + c, a, epoch); }
     }
-    publish(flag_b + j, epoch);
   }
 }
 
-struct FlowState { int *flags = nullptr; int cap = 0; int epoch = 0; int max_grid = 0; };
+struct FlowState { uint4 *flags = nullptr; int cap = 0; int epoch = 0; int max_grid = 0; };   // flags: the packet ring, 2 * nblk * NB packets
 static std::mutex g_flow_mu;
 static std::map<cudaStream_t, FlowState> g_flow;
 }  // namespace flow
@@ -1040,8 +1059,8 @@ static int chol_solve_flow(cudaStream_t s, int npad, const double *L, int ld, co
     if (ref.cap < 2 * nblk) {
       if (ref.flags) QB_CUDA_TRY(cudaFree(ref.flags));
       ref.cap = 2 * nblk + 64;
-      QB_CUDA_TRY(cudaMalloc(&ref.flags, sizeof(int) * ref.cap));
-      QB_CUDA_TRY(cudaMemsetAsync(ref.flags, 0, sizeof(int) * ref.cap, s));
+      QB_CUDA_TRY(cudaMalloc(&ref.flags, sizeof(uint4) * (size_t)ref.cap * flow::NB));
+      QB_CUDA_TRY(cudaMemsetAsync(ref.flags, 0, sizeof(uint4) * (size_t)ref.cap * flow::NB, s));
       ref.epoch = 0;
     }
     ref.epoch++;
@@ -1049,7 +1068,7 @@ static int chol_solve_flow(cudaStream_t s, int npad, const double *L, int ld, co
   }
   int grid = nblk < st.max_grid ? nblk : st.max_grid;
   int nblk_arg = nblk, ld_arg = ld, epoch = st.epoch;
-  int *flags = st.flags;
+  uint4 *flags = st.flags;
   void *args[] = {(void *)&L, (void *)&ld_arg, (void *)&invdiag, (void *)&v, (void *)&nblk_arg, (void *)&flags, (void *)&epoch};
   const bool prof = g_prof_on && prof_begin("flow::k_solve_flow", s);
   const cudaError_t err = cudaLaunchCooperativeKernel((const void *)flow::k_solve_flow, dim3(grid), dim3(flow::NT), args, flow::kSmemBytes, s);

@@ -1,4 +1,4 @@
-"""Per-kernel CUDA-event breakdown of one solve of a BASELINE single-problem config (c1 | c5 | grid<g>): launches and device time per
+"""Per-kernel CUDA-event breakdown of one solve of a BASELINE single-problem config (c1 | c3 | c5 | grid<g>): launches and device time per
 kernel name, next to the un-profiled wall time of the same solve (the difference is launch latency + host control flow)."""
 import ctypes as C
 import json
@@ -12,12 +12,14 @@ from qpalm_b200.interface import Qpalm, load_library
 which = sys.argv[1] if len(sys.argv) > 1 else "c1"
 if which == "c1":
     p = problems.random_qp(1000, 2000, 0.05, 0.007, seed=0)
+elif which == "c3":
+    p = problems.dense_qp(8000, 16000, seed=0)
 elif which == "c5":
     p = problems.nonconvex_random_qp(5000, 10000, seed=1)
 elif which.startswith("grid"):
     p = problems.grid_qp(int(which[4:] or 150), seed=0)
 else:
-    raise SystemExit("c1 | c5 | grid<g>")
+    raise SystemExit("c1 | c3 | c5 | grid<g>")
 lib = load_library("b200")
 
 
