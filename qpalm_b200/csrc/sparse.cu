@@ -412,9 +412,13 @@ int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *inf
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * tri_ld(kSmallMaxNf) * kSmallMaxNf)));
     attr_set = true;
   }
+  static bool dumped = false;
+  const bool dump = !dumped && getenv("QPALM_B200_LEVELS") != nullptr;
+  dumped = true;
   for (int l = 0; l < h.nlevels; l++) {
     const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
     const int mnf = h.lvl_max_nf[l], mns = h.lvl_max_ns[l];
+    if (dump) fprintf(stderr, "[qpalm_b200 levels] level %d: fronts %d max nf %d max ns %d\n", l, cnt, mnf, mns);
     if (cnt <= 0) continue;
     if (mnf <= kSmallMaxNf) {
       const size_t smem = sizeof(double) * (size_t)tri_ld(mnf) * mnf;
