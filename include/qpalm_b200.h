@@ -220,6 +220,9 @@ int qpalm_b200_get_stats(const QPALMWorkspace *work, QPALMB200Stats *out);
  * {"kernel": {"launches": L, "ms": T}, ...} into buf (returns the needed size when buf is NULL) and resets the log. */
 int qpalm_b200_prof_enable(const char *patterns);
 int qpalm_b200_prof_report(char *buf, size_t buflen);
+/* Debug: in-kernel phase clocks of the cluster-per-front factorization kernel (csrc/sparse.cu, mfc::k_mf_front), accumulated
+ * while QPALM_B200_MF_CLOCKS is set; copies 16 counters out and clears them (tools/prof_config.py names them). */
+int qpalm_b200_mf_clocks(unsigned long long *out16);
 
 /* y = A x  (A m x n, CSC, stype 0)              -- replaces mat_vec,       solver_interface.c:252-262
  * y = A' x                                      -- replaces mat_tpose_vec, solver_interface.c:264-274

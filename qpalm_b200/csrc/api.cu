@@ -400,6 +400,19 @@ static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0) return false;
   if (e->kkt) return false;   // KKT path: a changed row is rewritten and the system refactorised (kkt.cu)
   const bool flow = !e->sp && e->updown_flow_ok && e->npad >= 256;   // one-launch dataflow sweep, <= 64 ranks each (updown_flow.cu)
+  const bool gen = use_updown_gen(e);                                // generator-form passes, <= 32 ranks each (updown_gen.cu)
+  if (gen) {
+    if (e->updown_force) return true;
+    // STATIC model again: per pass a chain of npad/128 block steps of the k-column triangular solve (step time set by the
+    // 128 x 128 x k products of one SM), the tile-parallel apply pass over the factor, the small generator kernels and the
+    // refresh of the inverted diagonal blocks.  Measured on B200, see DESIGN.md section 4.
+    const double nblk = e->npad / 128.0, sz = (e->npad / 8064.0) * (e->npad / 8064.0);
+    const int full = k / 32, rem = k % 32;
+    const double pass32 = nblk * e->updown_gen_step_ms32 + 0.16 * sz + 0.12, pass8 = nblk * e->updown_gen_step_ms8 + 0.09 * sz + 0.12;
+    const double t_ud = full * pass32 + (rem > 8 ? pass32 : (rem > 0 ? pass8 : 0.0));
+    const double t_rf = (e->npad / 128.0) * 0.12 + ((double)e->n * e->n * e->n / 3.0) / 25e9;
+    return t_ud < t_rf;
+  }
   if (e->sh_world > 1 && !flow) return false;   // row-sharded: only the dataflow path allreduces the gathered rows
   if (!flow && k > (e->sp ? 8 * e->updown_max_rank : e->updown_max_rank)) return false;
   if (e->updown_force) return true;

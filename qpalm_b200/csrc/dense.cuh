@@ -49,6 +49,14 @@ int chol_updown_flow(cudaStream_t s, int npad, double *L, int ld, const double *
 int chol_updown_flow_max_rank();
 void chol_updown_flow_release(cudaStream_t s);
 
+// Generator-form pass (updown_gen.cu): the same result as chol_updown_flow for k <= 32 columns, reached by ONE triangular solve with
+// k right-hand sides (the only serial chain, npad / 128 steps) + fully parallel passes.  invdiag = inverses of the diagonal blocks
+// of the current L (input; refresh it afterwards with trtri_diag_blocks).  Returns 0 when it ran, 1 when unavailable.
+int chol_updown_gen(cudaStream_t s, int npad, double *L, int ld, const double *invdiag, const double *W, int ldw, int k, int kpos,
+                    int *info_dev);
+int chol_updown_gen_max_rank();
+void chol_updown_gen_release(cudaStream_t s);
+
 // L(lower) <- H(lower) + diag_add * I on the leading n x n block; pad block <- identity.
 int copy_lower_add_diag(cudaStream_t s, int n, int npad, const double *H, double *L, int ld, double diag_add);
 

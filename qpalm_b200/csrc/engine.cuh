@@ -109,7 +109,9 @@ struct Engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
   // tunables
   int updown_max_rank = 8;           // one sweep of the rank-k kernel
+  bool updown_gen_ok = true;         // cleared when the generator-form update pass (updown_gen.cu) cannot launch on this device
   bool updown_flow_ok = true;        // cleared when the cooperative dataflow sweep cannot launch on this device
+  double updown_gen_step_ms32 = 0.016, updown_gen_step_ms8 = 0.0045;   // static cost model: one 128-row block step of the k-column triangular solve (updown_gen.cu), k <= 32 / <= 8
   double updown_panel_ms = 0.0135, updown_panel_ms64 = 0.0179;   // static cost model: one panel step of the dataflow sweep, <= 32 / <= 64 ranks (B200)
   int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
   double last_updown_ms = -1.0;      // CUDA-event time of the most recent update/downdate call (sparse cost model)
@@ -159,6 +161,7 @@ int step_residuals(Engine *e, bool proximal, double gamma, double tau);  // a3 +
 int step_compact_lists(Engine *e);                                       // ordered enter[] / leave[] lists
 int step_newton_refactor(Engine *e, bool with_constraints, bool from_scratch, double beta, int nb_active);
 int step_newton_updown(Engine *e, int nb_enter, int nb_leave);
+bool use_updown_gen(const Engine *e);
 int step_newton_solve(Engine *e);                                        // d = -(L L')^{-1} dphi
 int step_commit_active(Engine *e);                                       // active_old <- active
 int step_linesearch(Engine *e, bool proximal, double gamma);             // Qd, Ad, eta, beta, tau (on device)

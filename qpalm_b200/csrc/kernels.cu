@@ -601,6 +601,34 @@ static bool use_updown_flow(const Engine *e) {
   return !e->sp && e->npad >= min_npad && e->updown_flow_ok;
 }
 
+// generator-form passes (updown_gen.cu): <= 32 columns each, entering and leaving rows share a pass; the inverted diagonal
+// blocks are refreshed after every pass (the next pass's triangular solve needs them, and so do the Newton solves)
+bool use_updown_gen(const Engine *e) {
+  const char *s = getenv("QPALM_B200_UPDOWN_GEN");      // read per call: the tests run both update paths in one process
+  const bool off = s && atoi(s) == 0;
+  return !off && !e->sp && e->npad >= 256 && e->updown_gen_ok;
+}
+static int updown_gen_lists(Engine *e, const int *pos, const double *pos_scale, bool pos_by_row, int npos,
+                            const int *neg, const double *neg_scale, bool neg_by_row, int nneg) {
+  const int KMAX = chol_updown_gen_max_rank();
+  int ip = 0, in = 0;
+  while (ip < npos || in < nneg) {
+    const int kp = (npos - ip < KMAX) ? npos - ip : KMAX;
+    const int kn = (nneg - in < KMAX - kp) ? nneg - in : KMAX - kp;
+    if (int r = gather_rows(e, pos + ip, pos_by_row ? pos_scale : pos_scale + ip, pos_by_row, kp, kp, 0)) return r;
+    if (int r = gather_rows(e, neg + in, neg_by_row ? neg_scale : neg_scale + in, neg_by_row, kn, kn, kp)) return r;
+    if (e->sh_world > 1) { if (int r = shard_allreduce(e->W, e->W, (size_t)e->ld * (kp + kn), false, e->stream)) return r; }
+    const int rc = chol_updown_gen(e->stream, e->npad, e->L, e->ld, e->invdiag, e->W, e->ld, kp + kn, kp, e->info_dev);
+    if (rc) return (rc == 1 && ip == 0 && in == 0) ? 1 : (rc < 0 ? rc : -999);
+    if (int r = trtri_diag_blocks(e->stream, e->npad, e->L, e->ld, e->invdiag)) return r;
+    e->n_updown++; e->updown_rank_sum += kp + kn;
+    e->dense_flops += 2.0 * (kp + kn) * (double)e->n * e->n;
+    e->alg_bytes += 3.0 * 8.0 * (double)e->n * (e->n + 1) / 2;
+    ip += kp; in += kn;
+  }
+  return 0;
+}
+
 // L <- chol(L L' + sum_enter w w' - sum_leave w w'): entering and leaving rows share sweeps of <= 64 columns
 // (weight pattern S = diag(+1.., -1..), see updown_flow.cu)
 static int updown_flow_lists(Engine *e, const int *pos, const double *pos_scale, bool pos_by_row, int npos,
@@ -630,6 +658,12 @@ static int updown_flow_lists(Engine *e, const int *pos, const double *pos_scale,
 // ldlupdate_entering_constraints / ldldowndate_leaving_constraints (solver_interface.c:407-441)
 int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
+  if (use_updown_gen(e)) {
+    const int rc = updown_gen_lists(e, e->enter, e->sqrt_sigma, true, nb_enter, e->leave, e->sqrt_sigma, true, nb_leave);
+    if (rc < 0) return rc;
+    if (rc == 0) { QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream)); return 0; }
+    e->updown_gen_ok = false;
+  }
   if (use_updown_flow(e)) {
     const int rc = updown_flow_lists(e, e->enter, e->sqrt_sigma, true, nb_enter, e->leave, e->sqrt_sigma, true, nb_leave);
     if (rc < 0) return rc;
@@ -667,6 +701,12 @@ int step_newton_updown(Engine *e, int nb_enter, int nb_leave) {
 // ldlupdate_sigma_changed (solver_interface.c:443-503): rank-k update with sqrt(sigma_new - sigma_old) * a_j
 int sigma_changed_update(Engine *e, int nb_changed) {
   QB_CUDA_TRY(cudaEventRecord(e->evs0, e->stream));
+  if (use_updown_gen(e)) {
+    const int rc = updown_gen_lists(e, e->changed, e->w_pos, false, nb_changed, nullptr, nullptr, false, 0);
+    if (rc < 0) return rc;
+    if (rc == 0) { QB_CUDA_TRY(cudaEventRecord(e->evs1, e->stream)); return 0; }
+    e->updown_gen_ok = false;
+  }
   if (use_updown_flow(e)) {
     const int rc = updown_flow_lists(e, e->changed, e->w_pos, false, nb_changed, nullptr, nullptr, false, 0);
     if (rc < 0) return rc;
@@ -2044,7 +2084,7 @@ void engine_destroy(Engine *e) {
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs0) cudaEventDestroy(e->evs0);
   if (e->evs1) cudaEventDestroy(e->evs1);
-  if (e->stream) { chol_solve_release(e->stream); chol_updown_flow_release(e->stream); cudaStreamDestroy(e->stream); }
+  if (e->stream) { chol_solve_release(e->stream); chol_updown_flow_release(e->stream); chol_updown_gen_release(e->stream); cudaStreamDestroy(e->stream); }
   delete e;
 }
 

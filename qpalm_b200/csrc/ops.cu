@@ -223,6 +223,18 @@ extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *
   static const int flow_min = [] { const char *s = getenv("QPALM_B200_UPDOWN_FLOW_MIN"); return s ? atoi(s) : 256; }();
   bool flow = npad >= flow_min;   // same dispatch as step_newton_updown: one dataflow launch per <= 64 columns
   const int chunk = flow ? chol_updown_flow_max_rank() : 8;
+  bool gen = use_updown_gen(e);   // ... preceded by the generator-form passes of <= 32 columns (updown_gen.cu)
+  for (int off = 0; off < k && !rc && gen; off += chol_updown_gen_max_rank()) {
+    const int kk = k - off < chol_updown_gen_max_rank() ? k - off : chol_updown_gen_max_rank();
+    std::vector<double> Wp((size_t)ld * kk, 0.0);
+    for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
+    QB_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    QB_CUDA_TRY(cudaMemcpy(e->W, Wp.data(), sizeof(double) * Wp.size(), cudaMemcpyHostToDevice));
+    rc = trtri_diag_blocks(e->stream, npad, e->L, ld, e->invdiag);
+    if (!rc) rc = chol_updown_gen(e->stream, npad, e->L, ld, e->invdiag, e->W, ld, kk, update ? kk : 0, e->info_dev);
+    if (rc == 1 && off == 0) { gen = false; rc = 0; }
+  }
+  if (gen) flow = false;
   for (int off = 0; off < k && !rc && flow; off += chunk) {
     const int kk = k - off < chunk ? k - off : chunk;
     std::vector<double> Wp((size_t)ld * kk, 0.0);
@@ -232,7 +244,7 @@ extern "C" int qpalm_b200_updown(c_int n_, c_int k_, c_float *L, const c_float *
     rc = chol_updown_flow(e->stream, npad, e->L, ld, e->W, ld, kk, update ? kk : 0, e->info_dev);
     if (rc == 1 && off == 0) { flow = false; rc = 0; }   // no cooperative launch here: per-panel kernels below
   }
-  for (int off = 0; off < k && !rc && !flow; off += 8) {
+  for (int off = 0; off < k && !rc && !flow && !gen; off += 8) {
     const int kk = k - off < 8 ? k - off : 8;
     std::vector<double> Wp((size_t)ld * 8, 0.0);
     for (int c = 0; c < kk; c++) for (int i = 0; i < n; i++) Wp[(size_t)i + (size_t)ld * c] = W[(size_t)i + (size_t)n * (off + c)];
@@ -433,10 +445,19 @@ extern "C" int qpalm_b200_bench_updown(c_int n_, c_int k_, c_int reps, double *m
   int rc = potrf_lower(s, n, L, n, X, info);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   float total = 0;
+  const char *genv = getenv("QPALM_B200_UPDOWN_GEN");
+  const bool gen = !(genv && atoi(genv) == 0);
   for (int r = 0; r < reps + 1 && !rc; r++) {
     cudaEventRecord(a, s);
-    rc = chol_updown_flow(s, n, L, n, W, n, k, k, info);
-    if (!rc) rc = chol_updown_flow(s, n, L, n, W, n, k, 0, info);
+    if (gen && k <= chol_updown_gen_max_rank()) {     // each pass with the refresh of the inverted diagonal blocks it needs
+      rc = chol_updown_gen(s, n, L, n, X, W, n, k, k, info);
+      if (!rc) rc = trtri_diag_blocks(s, n, L, n, X);
+      if (!rc) rc = chol_updown_gen(s, n, L, n, X, W, n, k, 0, info);
+      if (!rc) rc = trtri_diag_blocks(s, n, L, n, X);
+    } else {
+      rc = chol_updown_flow(s, n, L, n, W, n, k, k, info);
+      if (!rc) rc = chol_updown_flow(s, n, L, n, W, n, k, 0, info);
+    }
     cudaEventRecord(b, s);
     QB_CUDA_TRY(cudaEventSynchronize(b));
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
@@ -444,7 +465,7 @@ extern "C" int qpalm_b200_bench_updown(c_int n_, c_int k_, c_int reps, double *m
   }
   *ms_out = total / (2.0 * (reps > 0 ? reps : 1));
   int hinfo = 0; cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
-  chol_updown_flow_release(s);
+  chol_updown_flow_release(s); chol_updown_gen_release(s);
   cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); cudaFree(L); cudaFree(X); cudaFree(W); cudaFree(info);
   return rc ? rc : hinfo;
 }

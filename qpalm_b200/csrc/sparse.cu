@@ -405,13 +405,302 @@ __global__ void __launch_bounds__(256) k_mf_small(SpDev d, double *panels, doubl
   if (tid == 0 && bad) atomicExch(info, bad);
 }
 
+// ================================================================================================
+// numeric factorization, large fronts: ONE launch per level, one thread-block CLUSTER per front
+// ================================================================================================
+// The per-block launches above (k_mf_extend + per 32 columns k_mf_diag / k_mf_trsm / k_mf_syrk: 97 dependent block steps
+// at ~46 us each on the n = 90 000 grid problem) become one launch per level: the CTAs of a cluster share one front, meet
+// at hardware cluster barriers (release / acquire; data crosses CTAs through L2, read with ld.global.cg) and fronts of a
+// level no longer wait for each other between steps.  CTA 0 of a multi-CTA cluster is the CHAIN CTA: while the others
+// apply block kb's trailing update it brings the NEXT 32 x 32 diagonal block up to date and factors it in registers, so
+// the one-warp factorization is off the other CTAs' critical path.  Every floating-point operation is the one the
+// per-block kernels perform, in the same order: the two paths give bit-identical factors (tests/test_gpu_sparse.py).
+namespace mfc {
+constexpr int NT = 256;
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cta_count() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+
+struct Smem {
+  double Ls[32][33];
+  union {
+    struct { double As[32][65], Bs[32][65]; } t;     // trailing-update tile operands
+    struct { double Sl[32][33], Dn[32][33]; } c;     // chain CTA: slab of the next block's rows, next diagonal block
+  };
+};
+
+// 32 x 32 in-register factorization of the block held in B (global, ld nf) or Dn (shared), written to B
+__device__ __forceinline__ void factor_block(const SpDev &d, double *B, int nf, int w, int pcol0, const double (*Dn)[33], int *info) {
+  const int lane = threadIdx.x;
+  double row[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    row[j] = (lane < w && j <= lane) ? (Dn ? Dn[lane][j] : __ldcg(B + (size_t)lane + (size_t)j * nf)) : ((j == lane) ? 1.0 : 0.0);
+  double dl = 1.0, dinv = 1.0;
+  int badcol = -1;
+  if (d.sgn) {
+    const unsigned negmask = __ballot_sync(0xffffffffu, lane < w && d.sgn[pcol0 + lane] < 0);
+    chol32::fstep_signed<0>(row, lane, dl, negmask, badcol);
+  } else chol32::fstep<0>(row, lane, dl, dinv, badcol);
+#pragma unroll
+  for (int j = 0; j < 32; j++) if (lane < w && j < lane) B[(size_t)lane + (size_t)j * nf] = row[j];
+  if (lane < w) B[(size_t)lane + (size_t)lane * nf] = dl;
+  if (badcol >= 0 && badcol < w && lane == 0) atomicExch(info, 1 + pcol0);
+}
+
+// optional phase clocks (QPALM_B200_MF_CLOCKS=1; tools/prof_config.py prints them): thread 0 of CTA 0 and of CTA 1 of the first
+// front of each level add the clocks spent per phase
+__device__ unsigned long long g_mf_clk[16];
+#define MF_CLK(slot, who)                                                                                              \
+  do {                                                                                                                 \
+    if (clk_on && tid == 0 && cr == (who)) { const long long now_ = clock64(); atomicAdd(&g_mf_clk[slot], (unsigned long long)(now_ - t_last)); t_last = now_; } \
+  } while (0)
+
+__global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double *upd, int lvl_begin, int *info, int clocks) {
+  __shared__ Smem sm;
+  const int cr = (int)cta_rank(), cn = (int)cta_count();
+  const bool clk_on = clocks && cluster_id() == 0;
+  long long t_last = clock64();
+  const Front F = load_front(d, panels, upd, d.lvl_sn[lvl_begin + (int)cluster_id()]);
+  const int nf = F.nf, ns = F.ns;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+
+  // ---- extend-add: 16-column chunks of target columns, chunk q belongs to CTA q % cn (one owner per target entry,
+  //      children in their fixed order: no atomics, bit-reproducible)
+  const int nchunk = (nf + kExtT - 1) / kExtT;
+  for (int q = cr; q < nchunk; q += cn) {
+    const int c0 = q * kExtT, c1 = min(nf, c0 + kExtT);
+    for (int tc = max(c0, ns) + warp; tc < c1; tc += NW)
+      for (int i = tc + lane; i < nf; i += 32) *front_at(F, i, tc) = 0.0;
+  }
+  __syncthreads();
+  for (int ch = d.child_ptr[F.s]; ch < d.child_ptr[F.s + 1]; ch++) {
+    const int c = d.child_idx[ch];
+    const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
+    const int *rel = d.rel + cro;
+    const double *Uc = upd + d.upd_off[c];
+    // source columns of the child, 32 at a time per warp; the owner of target column rel[jc] takes it
+    for (int jb = warp * 32; jb < cnr; jb += NW * 32) {
+      const int tcl = (jb + lane < cnr) ? rel[jb + lane] : -1;
+      unsigned mine = __ballot_sync(0xffffffffu, tcl >= 0 && (tcl / kExtT) % cn == cr);
+      while (mine) {
+        const int b = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const int jc = jb + b, tc = __shfl_sync(0xffffffffu, tcl, b);
+        const double *src = Uc + (size_t)jc * cnr;
+        // eight independent gathers in flight per lane (a rolled loop pays two dependent L2 round trips per 32 entries)
+        for (int ic = jc + lane; ic < cnr; ic += 256) {
+          double *pt[8];
+          double sv[8], tv[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int iu = ic + 32 * u;
+            pt[u] = (iu < cnr) ? front_at(F, rel[iu], tc) : nullptr;
+            sv[u] = (iu < cnr) ? src[iu] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) tv[u] = pt[u] ? *pt[u] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; u++) if (pt[u]) *pt[u] = tv[u] + sv[u];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  MF_CLK(0, 0);
+  cluster_sync();
+  MF_CLK(1, 0);
+
+  // ---- block 0 of the panel
+  if (cr == 0 && warp == 0) factor_block(d, F.P, nf, min(32, ns), F.f, nullptr, info);
+  cluster_sync();
+  MF_CLK(2, 0);
+  if (clk_on && tid == 0 && cr == 1) t_last = clock64();
+
+  const int nkb = (ns + 31) / 32;
+  for (int kb = 0; kb < nkb; kb++) {
+    const int k0 = kb * 32, w = min(32, ns - k0), base = k0 + w;
+    if (base >= nf) break;                       // nothing below the last block (root front); uniform over the cluster
+    double *P = F.P;
+    // (a) the factored diagonal block, diagonal inverted, column signs folded in (as k_mf_trsm)
+    for (int t = tid; t < 32 * 32; t += NT) {
+      const int r = t & 31, c = t >> 5;
+      double v = (r < w && c <= r) ? __ldcg(P + (size_t)(k0 + r) + (size_t)(k0 + c) * nf) : ((r == c) ? 1.0 : 0.0);
+      if (r == c) v = 1.0 / v;
+      if (c < w) v *= sgn_of(d, F.f + k0 + c);
+      sm.Ls[r][c] = v;
+    }
+    __syncthreads();
+    MF_CLK(3, 0);
+    // (b) rows below: X <- X inv(L11') inv(S); 32-row chunks round-robin over the warps of the cluster, lane = row
+    for (int i0 = base + (cr * NW + warp) * 32; i0 < nf; i0 += cn * NW * 32) {
+      const int i = i0 + lane;
+      if (i < nf) {
+        double x[32];
+#pragma unroll
+        for (int t = 0; t < 32; t++) x[t] = (t < w) ? __ldcg(P + (size_t)i + (size_t)(k0 + t) * nf) : 0.0;
+        // right-looking order: as soon as x[u] is final every later column takes its term -- 31 - u independent FMAs per step
+        // instead of one 528-long dependent chain; each x[t] still accumulates u = 0, 1, ... in order (same bits as k_mf_trsm)
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+          x[u] *= sm.Ls[u][u];
+#pragma unroll
+          for (int t = u + 1; t < 32; t++) x[t] = fma(-x[u], sm.Ls[t][u], x[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 32; t++) if (t < w) P[(size_t)i + (size_t)(k0 + t) * nf] = x[t];
+      }
+    }
+    MF_CLK(4, 0);
+    cluster_sync();
+    MF_CLK(5, 0);
+    if (clk_on && tid == 0 && cr == 1) t_last = clock64();
+    // (c) trailing update F(i, j) -= sum_t P(i, k0 + t) s_t P(j, k0 + t), i >= j >= base
+    const bool lookahead = cn > 1 && base < ns;   // the chain CTA owns the next diagonal block
+    if (cn > 1 && cr == 0) {
+      if (lookahead) {
+        const int wn = min(32, ns - base);
+        for (int t = tid; t < 32 * 32; t += NT) {
+          const int r = t & 31, c = t >> 5;        // Sl[c][r] = P(base + r, k0 + c)
+          sm.c.Sl[c][r] = (c < w && r < wn) ? __ldcg(P + (size_t)(base + r) + (size_t)(k0 + c) * nf) : 0.0;
+        }
+        double old[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int c = warp + 8 * q;
+          old[q] = (lane < wn && c <= lane) ? __ldcg(P + (size_t)(base + lane) + (size_t)(base + c) * nf) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int c = warp + 8 * q;
+          double acc = 0.0;
+#pragma unroll 8
+          for (int t = 0; t < 32; t++) acc = fma(sm.c.Sl[t][lane], sgn_of(d, F.f + k0 + min(t, w - 1)) * sm.c.Sl[t][c], acc);
+          sm.c.Dn[lane][c] = old[q] - acc;
+        }
+        __syncthreads();
+        if (warp == 0) factor_block(d, P + (size_t)base + (size_t)base * nf, nf, wn, F.f + base, sm.c.Dn, info);
+      }
+    } else {
+      const int T = (nf - base + 63) / 64, ntile = T * (T + 1) / 2;
+      const int nworker = cn > 1 ? cn - 1 : 1, me = cn > 1 ? cr - 1 : 0;
+      const int tx = tid & 15, ty = tid >> 4;
+      for (int idx = me; idx < ntile; idx += nworker) {
+        int by = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while ((by + 1) * (by + 2) / 2 <= idx) by++;
+        while (by * (by + 1) / 2 > idx) by--;
+        const int bz = idx - by * (by + 1) / 2;
+        const int i0 = base + by * 64, j0 = base + bz * 64;
+        __syncthreads();      // the previous tile's operands are no longer needed
+        for (int t = tid; t < 32 * 64; t += NT) {
+          const int r = t & 63, c = t >> 6;
+          sm.t.As[c][r] = (c < w && i0 + r < nf) ? __ldcg(P + (size_t)(i0 + r) + (size_t)(k0 + c) * nf) : 0.0;
+          sm.t.Bs[c][r] = (c < w && j0 + r < nf) ? sgn_of(d, F.f + k0 + c) * __ldcg(P + (size_t)(j0 + r) + (size_t)(k0 + c) * nf) : 0.0;
+        }
+        // old values of the tile requested before the products
+        double old[4][4];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
+            old[a][b] = (i < nf && j < nf && i >= j) ? __ldcg(front_at(F, i, j)) : 0.0;
+          }
+        __syncthreads();
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 8
+        for (int t = 0; t < 32; t++) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) { av[a] = sm.t.As[t][tx + 16 * a]; bv[a] = sm.t.Bs[t][ty + 16 * a]; }
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int j = j0 + ty + 16 * b;
+          if (j >= nf) continue;
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int i = i0 + tx + 16 * a;
+            if (i >= nf || i < j) continue;
+            if (lookahead && i < base + min(32, ns - base)) continue;      // the chain CTA writes the next diagonal block
+            *front_at(F, i, j) = old[a][b] - acc[a][b];
+          }
+        }
+      }
+      if (cn == 1 && base < ns) {               // single-CTA cluster: factor the next block after its update
+        __syncthreads();
+        if (warp == 0) factor_block(d, P + (size_t)base + (size_t)base * nf, nf, min(32, ns - base), F.f + base, nullptr, info);
+      }
+    }
+    MF_CLK(6, 0); MF_CLK(7, 1);
+    cluster_sync();
+    MF_CLK(8, 0); MF_CLK(9, 1);
+    if (clk_on && tid == 0 && cr == 0) atomicAdd(&g_mf_clk[10], 1ull);
+  }
+  if (clk_on && tid == 0 && cr == 0) atomicAdd(&g_mf_clk[11], 1ull);
+}
+}  // namespace mfc
+
+static int launch_front_level(SparseChol *sc, cudaStream_t st, double *panels, int lvl_begin, int cnt, int mnf, int *info_dev) {
+  // cluster size: a power of two <= 16, one wave of CTAs (one per SM), no more CTAs than chain + trailing tiles need
+  const int T = cdiv(max(mnf - 32, 1), 64), ntile = T * (T + 1) / 2;
+  int cn = 1;
+  while (cn < 16 && cnt * (cn * 2) <= 148 && cn < ntile + 1) cn *= 2;
+  static int max_cluster = -1;
+  if (max_cluster < 0) {
+    max_cluster = 8;
+    if (cudaFuncSetAttribute(mfc::k_mf_front, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) max_cluster = 16;
+    else (void)cudaGetLastError();
+  }
+  int cap = max_cluster;
+  if (const char *e = getenv("QPALM_B200_MF_CLUSTER")) cap = max(1, min(max_cluster, atoi(e)));   // tests: force small clusters
+  while (cn > cap) cn /= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(cnt * cn)); cfg.blockDim = dim3(mfc::NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cn; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  const bool prof = g_prof_on && prof_begin("k_mf_front", st);
+  static const int clocks = getenv("QPALM_B200_MF_CLOCKS") ? 1 : 0;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, mfc::k_mf_front, sc->d, panels, sc->upd, lvl_begin, info_dev, clocks);
+  ++g_kernel_launches;
+  if (prof) prof_end(st);
+  QB_CUDA_TRY(err);
+  return 0;
+}
+
+// debug: reads and clears the phase clocks of mfc::k_mf_front (12 counters)
+extern "C" int qpalm_b200_mf_clocks(unsigned long long *out16) {
+  QB_CUDA_TRY(cudaDeviceSynchronize());
+  QB_CUDA_TRY(cudaMemcpyFromSymbol(out16, mfc::g_mf_clk, sizeof(unsigned long long) * 16));
+  unsigned long long z[16] = {0};
+  QB_CUDA_TRY(cudaMemcpyToSymbol(mfc::g_mf_clk, z, sizeof(z)));
+  return 0;
+}
+
 int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *info_dev) {
   const SymHost &h = sc->h;
   static bool attr_set = false;
+  static bool per_block = false;      // QPALM_B200_MF_PER_BLOCK=1: the per-block launches (A/B and bit-identity tests)
   if (!attr_set) {
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * tri_ld(kSmallMaxNf) * kSmallMaxNf)));
     attr_set = true;
   }
+  { const char *e = getenv("QPALM_B200_MF_PER_BLOCK"); per_block = e && atoi(e) != 0; }
   static bool dumped = false;
   const bool dump = !dumped && getenv("QPALM_B200_LEVELS") != nullptr;
   dumped = true;
@@ -425,8 +714,11 @@ int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *inf
       QB_LAUNCH(k_mf_small, cnt, mnf <= 32 ? 64 : (mnf <= 64 ? 128 : 256), smem, st, sc->d, panels, sc->upd, b, info_dev);
       continue;
     }
-    if (l > 0) { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
-    else { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
+    if (!per_block) {
+      if (int rc = launch_front_level(sc, st, panels, b, cnt, mnf, info_dev)) return rc;
+      continue;
+    }
+    { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
     for (int kb = 0; kb * 32 < mns; kb++) {
       QB_LAUNCH(k_mf_diag, cnt, 32, 0, st, sc->d, panels, b, kb, info_dev);
       const int rest = mnf - kb * 32 - 1;   // rows below the block (upper bound over the level)

@@ -62,6 +62,34 @@ def test_factorization_is_bit_reproducible():
     assert np.array_equal(L1, L2) and np.array_equal(d1, d2)
 
 
+@pytest.mark.parametrize("cluster", ["1", "2", "8", "16"])
+@pytest.mark.parametrize("name,make", [("grid70", lambda: problems.grid_qp(70, seed=6)),
+                                       ("rand_one_front", lambda: problems.random_qp(300, 500, 0.2, 0.1, seed=4)),
+                                       ("rand_one_front_700", lambda: problems.random_qp(700, 900, 0.2, 0.1, seed=5))],
+                         ids=["grid70", "rand_one_front", "rand_one_front_700"])
+def test_cluster_front_kernel_equals_per_block_launches(name, make, cluster):
+    """Fronts above the shared-memory size are factored by ONE launch per level (a thread-block cluster per front, chain CTA with
+    look-ahead, mfc::k_mf_front); the per-block launches (k_mf_extend / k_mf_diag / k_mf_trsm / k_mf_syrk) remain behind
+    QPALM_B200_MF_PER_BLOCK=1.  Same operations in the same order: the factors must be bit-identical for every cluster size."""
+    p = make()
+    rng = np.random.default_rng(21)
+    sigma = 0.5 + 20 * rng.random(p.m); act = (rng.random(p.m) < 0.5).astype(np.int64); rhs = rng.standard_normal(p.n)
+    out = {}
+    for mode, env in (("block", {"QPALM_B200_MF_PER_BLOCK": "1"}), ("cluster", {"QPALM_B200_MF_PER_BLOCK": "0", "QPALM_B200_MF_CLUSTER": cluster})):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            out[mode] = sparse_newton(p.Q, p.A, sigma, act, 1e-3, rhs, want_factor=True)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert np.array_equal(out["block"][1], out["cluster"][1])
+    assert np.array_equal(out["block"][0], out["cluster"][0])
+    H = _dense_H(p, sigma, act, 1e-3)
+    dref = np.linalg.solve(H, rhs)
+    assert np.max(np.abs(out["cluster"][0] - dref)) <= 1e-9 * max(1.0, np.max(np.abs(dref)))
+
+
 @pytest.mark.parametrize("name,make", [("grid31", lambda: problems.grid_qp(31, seed=2)),
                                        ("rand_sparse", lambda: problems.random_qp(150, 260, 0.02, 0.01, seed=3)),
                                        ("grid70", lambda: problems.grid_qp(70, seed=6))], ids=["grid31", "rand_sparse", "grid70"])

@@ -51,3 +51,17 @@ tot_ms = sum(v["ms"] for v in rep.values()); tot_l = sum(v["launches"] for v in 
 print(f"profiled: {tot_l} launches ({tot_l / max(1, r.iter):.1f} per iteration), device time in kernels {tot_ms:.2f} ms")
 for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:40]:
     print(f"  {k:34s} launches {v['launches']:6d}  ms {v['ms']:9.3f}  mean_us {1e3 * v['ms'] / v['launches']:8.2f}")
+
+if os.environ.get("QPALM_B200_MF_CLOCKS"):
+    lib.qpalm_b200_mf_clocks.argtypes = [C.POINTER(C.c_ulonglong)]
+    buf = (C.c_ulonglong * 16)()
+    lib.qpalm_b200_mf_clocks(buf)      # clear what the solves above accumulated
+    solve(False)
+    lib.qpalm_b200_mf_clocks(buf)
+    names = ["extend", "wait B0", "block 0 + sync", "Ls load", "trsm", "wait B1", "chain (CTA 0)", "tiles (CTA 1)", "wait B2 (CTA 0)",
+             "wait B2 (CTA 1)"]
+    steps, launches = max(1, buf[10]), max(1, buf[11])
+    print(f"k_mf_front phase clocks of the first front of each level: {launches} launches, {steps} block steps")
+    for i, nm in enumerate(names):
+        per = "launch" if i < 3 else "step"
+        print(f"  {nm:18s} {buf[i] / (launches if i < 3 else steps):10.0f} clocks per {per}   total {buf[i] / 1.965e6:9.2f} ms")
