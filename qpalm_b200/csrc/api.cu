@@ -406,10 +406,12 @@ static bool prefer_updown(const Engine *e, int k) {
     // STATIC model again: per pass a chain of npad/128 block steps of the k-column triangular solve (step time set by the
     // 128 x 128 x k products of one SM), the tile-parallel apply pass over the factor, the small generator kernels and the
     // refresh of the inverted diagonal blocks.  Measured on B200, see DESIGN.md section 4.
+    // pass time (ms) = a * (npad / 128) + b * (npad / 8064)^2 + c, fitted to the measured passes at npad = 1024 and 8064:
+    //   <= 8 columns 0.11 / 0.48 ms, <= 16 columns 0.13 / 0.56 ms, <= 32 columns 0.17 / 0.95 ms  (the dataflow sweep: 0.43 / 3.2 ms)
     const double nblk = e->npad / 128.0, sz = (e->npad / 8064.0) * (e->npad / 8064.0);
+    const double pass8 = 0.0030 * nblk + 0.21 * sz + 0.085, pass16 = 0.0035 * nblk + 0.25 * sz + 0.09, pass32 = 0.0065 * nblk + 0.42 * sz + 0.12;
     const int full = k / 32, rem = k % 32;
-    const double pass32 = nblk * e->updown_gen_step_ms32 + 0.16 * sz + 0.12, pass8 = nblk * e->updown_gen_step_ms8 + 0.09 * sz + 0.12;
-    const double t_ud = full * pass32 + (rem > 8 ? pass32 : (rem > 0 ? pass8 : 0.0));
+    const double t_ud = e->updown_gen_scale * (full * pass32 + (rem > 16 ? pass32 : (rem > 8 ? pass16 : (rem > 0 ? pass8 : 0.0))));
     const double t_rf = (e->npad / 128.0) * 0.12 + ((double)e->n * e->n * e->n / 3.0) / 25e9;
     return t_ud < t_rf;
   }
@@ -653,9 +655,14 @@ extern "C" void qpalm_solve(QPALMWorkspace *work) {
         e->alg_bytes += 2.0 * BA + BQ + 8.0 * (38.0 * m + 26.0 * n);
         goto end_of_iteration;
       }
-      if ((sv->reset_newton && na) || (double)(ne + nl) > rank_limit) { need_refactor = true; from_scratch = sv->reset_newton != 0; }
+      // Beyond its rank limit the reference refactorises (newton.c:98-108: a cost heuristic for cholmod_updown on a CPU).  The
+      // generator-form passes (updown_gen.cu) cost a fraction of a refactorisation, so the device cost model may still take the
+      // update there -- the same matrix either way.  A zero limit (max_rank_update = 0: "always refactorise") is honoured.
+      const bool over = (double)(ne + nl) > rank_limit;
+      const bool over_but_update = over && !sv->reset_newton && na && rank_limit > 0 && use_updown_gen(e) && prefer_updown(e, ne + nl);
+      if ((sv->reset_newton && na) || (over && !over_but_update)) { need_refactor = true; from_scratch = sv->reset_newton != 0; }
       else if (na) {
-        if (ne + nl > 0) { if (prefer_updown(e, ne + nl)) do_updown = true; else need_refactor = true; }
+        if (ne + nl > 0) { if (over_but_update || prefer_updown(e, ne + nl)) do_updown = true; else need_refactor = true; }
       } else factor_q = true;
       if (trace) fprintf(stderr, "[qpalm_b200 trace] iter %ld out %ld active %d enter %d leave %d -> %s\n", (long)iter, (long)iter_out, na, ne, nl,
                          do_updown ? "rank update" : (need_refactor ? (from_scratch ? "refactor (scratch)" : "refactor (incremental H)") : (factor_q ? "factor Q" : "reuse factor")));

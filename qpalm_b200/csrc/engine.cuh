@@ -111,7 +111,7 @@ struct Engine {
   int updown_max_rank = 8;           // one sweep of the rank-k kernel
   bool updown_gen_ok = true;         // cleared when the generator-form update pass (updown_gen.cu) cannot launch on this device
   bool updown_flow_ok = true;        // cleared when the cooperative dataflow sweep cannot launch on this device
-  double updown_gen_step_ms32 = 0.016, updown_gen_step_ms8 = 0.0045;   // static cost model: one 128-row block step of the k-column triangular solve (updown_gen.cu), k <= 32 / <= 8
+  double updown_gen_scale = 1.0;     // static cost model of the generator-form passes (api.cu prefer_updown): scale factor, QPALM_B200_UPDOWN_GEN_SCALE
   double updown_panel_ms = 0.0135, updown_panel_ms64 = 0.0179;   // static cost model: one panel step of the dataflow sweep, <= 32 / <= 64 ranks (B200)
   int updown_force = 0;              // QPALM_B200_UPDOWN_FORCE=1: bypass the cost model (tests)
   double last_updown_ms = -1.0;      // CUDA-event time of the most recent update/downdate call (sparse cost model)

@@ -2056,6 +2056,7 @@ static int engine_create_impl(Engine *e, Engine **out, int n, int m, const long 
   e->launches0 = g_kernel_launches;
   if (const char *s = getenv("QPALM_B200_UPDOWN_MAX_RANK")) e->updown_max_rank = atoi(s);
   if (const char *s = getenv("QPALM_B200_UPDOWN_FORCE")) e->updown_force = atoi(s);
+  if (const char *s = getenv("QPALM_B200_UPDOWN_GEN_SCALE")) e->updown_gen_scale = atof(s);
   if (const char *s = getenv("QPALM_B200_UPDOWN_PANEL_MS")) { e->updown_panel_ms = atof(s); e->updown_panel_ms64 = 1.33 * e->updown_panel_ms; }
   QB_CUDA_TRY(cudaDeviceSynchronize());
   lap("factor storage + scratch");

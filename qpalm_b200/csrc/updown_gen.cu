@@ -67,8 +67,15 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 template <int KW>
 __global__ void __launch_bounds__(NT, 1)
 k_fwd_multi(const double *__restrict__ L, int ld, const double *__restrict__ X, const double *__restrict__ W, int ldw, int k,
-            double *What, int npad, double *Tdump, int nblk, uint4 *packets, int epoch) {
+            double *What, int npad, double *Tdump, int nblk, uint4 *packets, int epoch, int kt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // the k right-hand sides are independent: blockIdx.y selects a group of KW of the pass's kt columns (its own CTAs, packets
+  // and chain), so a 32-column pass runs as two 16-column solves side by side on twice the SMs
+  {
+    const int c0 = (int)blockIdx.y * KW;
+    W += (size_t)c0 * ldw; What += (size_t)c0 * npad; Tdump += (size_t)c0 * NB; packets += (size_t)blockIdx.y * npad * KW;
+    k = max(0, min(KW, k - c0));
+  }
   constexpr int WS = FwdSmem<KW>::WS, XLD = FwdSmem<KW>::XLD, NN = KW / 8, NP = NB * KW / NT;
   double *Xs = reinterpret_cast<double *>(smem_raw);   // inverse of the current diagonal block, column-major, ld XLD
   double *ws = Xs + XLD * NB;                          // incoming What block  [128][WS]
@@ -118,7 +125,7 @@ k_fwd_multi(const double *__restrict__ L, int ld, const double *__restrict__ X, 
       }
       __syncthreads();
       if (j >= 1) {      // running sums before tile (i, j): the start of the row recurrence in k_gen_apply
-        double *dp = Tdump + (size_t)tile_id(i, j) * KW * NB;
+        double *dp = Tdump + (size_t)tile_id(i, j) * kt * NB;
 #pragma unroll
         for (int mb = 0; mb < 2; mb++)
 #pragma unroll
@@ -139,7 +146,7 @@ k_fwd_multi(const double *__restrict__ L, int ld, const double *__restrict__ X, 
       }
     }
     if (i >= 1) {
-      double *dp = Tdump + (size_t)tile_id(i, i) * KW * NB;
+      double *dp = Tdump + (size_t)tile_id(i, i) * kt * NB;
 #pragma unroll
       for (int mb = 0; mb < 2; mb++)
 #pragma unroll
@@ -344,45 +351,47 @@ struct State {
   uint4 *packets = nullptr;
   double *buf = nullptr;        // What | Z | D | G
   double *tdump = nullptr;
-  int cap_npad = 0, epoch = 0, max_grid[2] = {0, 0};
+  int cap_npad = 0, epoch = 0, max_grid[3] = {0, 0, 0};
 };
 static std::mutex g_mu;
 static std::map<cudaStream_t, State> g_state;
 
-template <int KW>
+template <int KT, int KW>     // KT columns per pass, solved as KT / KW independent groups
 static int run(cudaStream_t s, State &st, int slot, int npad, double *L, int ld, const double *X, const double *W, int ldw, int k, int kpos,
                int *info_dev) {
+  constexpr int NS = KT / KW;
   if (st.max_grid[slot] == 0) {
     int dev = 0, coop = 0, sms = 0, per_sm = 0;
     QB_CUDA_TRY(cudaGetDevice(&dev));
     QB_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     QB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     QB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_multi<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<KW>::bytes));
-    QB_CUDA_TRY(cudaFuncSetAttribute(k_gen_apply<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ApplySmem<KW>::bytes));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_gen_apply<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ApplySmem<KT>::bytes));
     QB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd_multi<KW>, NT, FwdSmem<KW>::bytes));
     st.max_grid[slot] = (coop && per_sm > 0) ? sms * per_sm : -1;
   }
-  if (st.max_grid[slot] <= 0) return 1;
+  if (st.max_grid[slot] < NS) return 1;
   const int nblk = npad / NB, nblocks = npad / GB;
   double *What = st.buf, *Z = What + (size_t)npad * 32, *D = Z + (size_t)npad * 32, *G = D + npad;
   {
-    const int grid = nblk < st.max_grid[slot] ? nblk : st.max_grid[slot];
-    int ld_a = ld, ldw_a = ldw, k_a = k, npad_a = npad, nblk_a = nblk, epoch = st.epoch;
+    const int gmax = st.max_grid[slot] / NS;
+    const int grid = nblk < gmax ? nblk : gmax;
+    int ld_a = ld, ldw_a = ldw, k_a = k, npad_a = npad, nblk_a = nblk, epoch = st.epoch, kt = KT;
     uint4 *pk = st.packets;
     double *td = st.tdump;
     void *args[] = {(void *)&L, (void *)&ld_a, (void *)&X, (void *)&W, (void *)&ldw_a, (void *)&k_a, (void *)&What, (void *)&npad_a,
-                    (void *)&td, (void *)&nblk_a, (void *)&pk, (void *)&epoch};
+                    (void *)&td, (void *)&nblk_a, (void *)&pk, (void *)&epoch, (void *)&kt};
     const bool prof = g_prof_on && prof_begin("udgen::k_fwd_multi", s);
-    const cudaError_t err = cudaLaunchCooperativeKernel((const void *)k_fwd_multi<KW>, dim3(grid), dim3(NT), args, FwdSmem<KW>::bytes, s);
+    const cudaError_t err = cudaLaunchCooperativeKernel((const void *)k_fwd_multi<KW>, dim3(grid, NS), dim3(NT), args, FwdSmem<KW>::bytes, s);
     if (prof) prof_end(s);
     if (err != cudaSuccess) { (void)cudaGetLastError(); st.max_grid[slot] = -1; return 1; }
     ++g_kernel_launches;
   }
-  QB_LAUNCH(k_gen_gram<KW>, nblocks, 256, 0, s, What, npad, G);
-  QB_LAUNCH(k_gen_scan<KW>, 1, KW * KW, 0, s, G, nblocks, k, kpos);
-  QB_LAUNCH(k_gen_rows<KW>, nblocks, 32, 0, s, What, npad, G, D, Z, info_dev);
+  QB_LAUNCH(k_gen_gram<KT>, nblocks, 256, 0, s, What, npad, G);
+  QB_LAUNCH(k_gen_scan<KT>, 1, KT * KT, 0, s, G, nblocks, k, kpos);
+  QB_LAUNCH(k_gen_rows<KT>, nblocks, 32, 0, s, What, npad, G, D, Z, info_dev);
   const int ntile = nblk * (nblk + 1) / 2;
-  QB_LAUNCH(k_gen_apply<KW>, ntile, NB, ApplySmem<KW>::bytes, s, L, ld, W, ldw, k, What, Z, D, npad, st.tdump);
+  QB_LAUNCH(k_gen_apply<KT>, ntile, NB, ApplySmem<KT>::bytes, s, L, ld, W, ldw, k, What, Z, D, npad, st.tdump);
   QB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -414,8 +423,9 @@ int chol_updown_gen(cudaStream_t s, int npad, double *L, int ld, const double *i
     st.epoch = 0;
   }
   st.epoch++;
-  return k <= 8 ? run<8>(s, st, 0, npad, L, ld, invdiag, W, ldw, k, kpos, info_dev)
-                : run<32>(s, st, 1, npad, L, ld, invdiag, W, ldw, k, kpos, info_dev);
+  if (k <= 8) return run<8, 8>(s, st, 0, npad, L, ld, invdiag, W, ldw, k, kpos, info_dev);
+  if (k <= 16) return run<16, 8>(s, st, 1, npad, L, ld, invdiag, W, ldw, k, kpos, info_dev);
+  return run<32, 16>(s, st, 2, npad, L, ld, invdiag, W, ldw, k, kpos, info_dev);
 }
 
 void chol_updown_gen_release(cudaStream_t s) {
