@@ -44,6 +44,7 @@ struct SparseChol {
   int *mark = nullptr;        // nsuper
   int small_nf = 0;           // fronts up to this size use the shared-memory kernel
   int small_smem_max = 0;
+  bool no_cluster = false;    // set when a cluster launch of mfc::k_mf_front was refused on this device / partition
 };
 
 template <typename T>
@@ -469,51 +470,43 @@ __global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
 
-  // ---- extend-add: 16-column chunks of target columns, chunk q belongs to CTA q % cn (one owner per target entry,
-  //      children in their fixed order: no atomics, bit-reproducible)
-  const int nchunk = (nf + kExtT - 1) / kExtT;
-  for (int q = cr; q < nchunk; q += cn) {
-    const int c0 = q * kExtT, c1 = min(nf, c0 + kExtT);
-    for (int tc = max(c0, ns) + warp; tc < c1; tc += NW)
-      for (int i = tc + lane; i < nf; i += 32) *front_at(F, i, tc) = 0.0;
-  }
-  __syncthreads();
+  // ---- extend-add.  Within one child every target entry receives exactly one source entry, so the child's lower triangle is
+  //      cut into (32-row segment, source column) items dealt round-robin to ALL warps of the cluster, eight items in flight
+  //      per warp; the children follow each other in their fixed order with a cluster barrier between them (no atomics,
+  //      bit-reproducible).  (Column-per-warp with an owner CTA per target column left most warps idle on the small clusters:
+  //      75 us per level against 33 us for the per-block kernel's full grid.)
+  const int gw = cr * NW + warp, GW = cn * NW;
+  for (int tc = ns + gw; tc < nf; tc += GW)
+    for (int i = tc + lane; i < nf; i += 32) F.U[(size_t)(i - ns) + (size_t)(tc - ns) * F.nr] = 0.0;
+  cluster_sync();
   for (int ch = d.child_ptr[F.s]; ch < d.child_ptr[F.s + 1]; ch++) {
     const int c = d.child_idx[ch];
     const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
     const int *rel = d.rel + cro;
     const double *Uc = upd + d.upd_off[c];
-    // source columns of the child, 32 at a time per warp; the owner of target column rel[jc] takes it
-    for (int jb = warp * 32; jb < cnr; jb += NW * 32) {
-      const int tcl = (jb + lane < cnr) ? rel[jb + lane] : -1;
-      unsigned mine = __ballot_sync(0xffffffffu, tcl >= 0 && (tcl / kExtT) % cn == cr);
-      while (mine) {
-        const int b = __ffs(mine) - 1;
-        mine &= mine - 1;
-        const int jc = jb + b, tc = __shfl_sync(0xffffffffu, tcl, b);
-        const double *src = Uc + (size_t)jc * cnr;
-        // eight independent gathers in flight per lane (a rolled loop pays two dependent L2 round trips per 32 entries)
-        for (int ic = jc + lane; ic < cnr; ic += 256) {
-          double *pt[8];
-          double sv[8], tv[8];
+    const int nS = (cnr + 31) >> 5, nitem = 32 * (nS * (nS + 1) / 2);   // item -> (S, jc): rows 32 S + lane, column jc < 32 (S + 1)
+    for (int it0 = gw; it0 < nitem; it0 += GW * 8) {
+      double *pt[8];
+      double sv[8], tv[8];
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int iu = ic + 32 * u;
-            pt[u] = (iu < cnr) ? front_at(F, rel[iu], tc) : nullptr;
-            sv[u] = (iu < cnr) ? src[iu] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) tv[u] = pt[u] ? *pt[u] : 0.0;
-#pragma unroll
-          for (int u = 0; u < 8; u++) if (pt[u]) *pt[u] = tv[u] + sv[u];
-        }
+      for (int u = 0; u < 8; u++) {
+        const int it = it0 + GW * u, blk = it >> 5;
+        int S = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+        while ((S + 1) * (S + 2) / 2 <= blk) S++;
+        while (S * (S + 1) / 2 > blk) S--;
+        const int jc = ((blk - S * (S + 1) / 2) << 5) + (it & 31), ic = (S << 5) + lane;
+        const bool ok = it < nitem && jc < cnr && ic < cnr && ic >= jc;
+        pt[u] = ok ? front_at(F, rel[ic], rel[jc]) : nullptr;
+        sv[u] = ok ? Uc[(size_t)ic + (size_t)jc * cnr] : 0.0;
       }
+#pragma unroll
+      for (int u = 0; u < 8; u++) tv[u] = pt[u] ? __ldcg(pt[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (pt[u]) *pt[u] = tv[u] + sv[u];
     }
-    __syncthreads();
+    cluster_sync();
   }
   MF_CLK(0, 0);
-  cluster_sync();
-  MF_CLK(1, 0);
 
   // ---- block 0 of the panel
   if (cr == 0 && warp == 0) factor_block(d, F.P, nf, min(32, ns), F.f, nullptr, info);
@@ -677,9 +670,12 @@ static int launch_front_level(SparseChol *sc, cudaStream_t st, double *panels, i
   const bool prof = g_prof_on && prof_begin("k_mf_front", st);
   static const int clocks = getenv("QPALM_B200_MF_CLOCKS") ? 1 : 0;
   const cudaError_t err = cudaLaunchKernelEx(&cfg, mfc::k_mf_front, sc->d, panels, sc->upd, lvl_begin, info_dev, clocks);
-  ++g_kernel_launches;
   if (prof) prof_end(st);
-  QB_CUDA_TRY(err);
+  if (err != cudaSuccess) {   // e.g. a partition that cannot co-schedule the cluster: the caller takes the per-block launches
+    (void)cudaGetLastError();
+    return 1;
+  }
+  ++g_kernel_launches;
   return 0;
 }
 
@@ -714,9 +710,11 @@ int sparse_chol_factor(SparseChol *sc, cudaStream_t st, double *panels, int *inf
       QB_LAUNCH(k_mf_small, cnt, mnf <= 32 ? 64 : (mnf <= 64 ? 128 : 256), smem, st, sc->d, panels, sc->upd, b, info_dev);
       continue;
     }
-    if (!per_block) {
-      if (int rc = launch_front_level(sc, st, panels, b, cnt, mnf, info_dev)) return rc;
-      continue;
+    if (!per_block && !sc->no_cluster) {
+      const int rc = launch_front_level(sc, st, panels, b, cnt, mnf, info_dev);
+      if (rc == 0) continue;
+      if (rc < 0) return rc;
+      sc->no_cluster = true;       // nothing of this level has run: fall through to the per-block launches, now and later
     }
     { dim3 g(cnt, cdiv(mnf, kExtT)); QB_LAUNCH(k_mf_extend, g, 256, 0, st, sc->d, panels, sc->upd, b); }
     for (int kb = 0; kb * 32 < mns; kb++) {
