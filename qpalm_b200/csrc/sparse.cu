@@ -755,6 +755,7 @@ __device__ __forceinline__ double div_by_rcp(double x, double l, double r) {
   return fma(fma(-q, l, x), r, q);
 }
 
+template <bool BIG>   // BIG: levels with fronts above 64 rows (256 threads); the leaf levels keep the small-register loop
 __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restrict__ panels, double *v, double *uvec, int lvl_begin) {
   extern __shared__ double fsh[];
   __shared__ double blk[32][33];
@@ -791,18 +792,32 @@ __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restric
     }
     __syncthreads();
     for (int i = k0 + w + tid; i < nf; i += blockDim.x) {
-      // 8 independent loads in flight per thread (a rolled loop pays one L2 round trip per column)
       const double *Pi = P + (size_t)i + (size_t)k0 * nf;
       double a0 = fsh[i], a1 = 0.0;
-      int t = 0;
-      for (; t + 8 <= w; t += 8) {
-        double pv[8];
+      if constexpr (BIG) {
+        // all (<= 32) loads of the row in flight at once: the rolled loop of 8-column batches below pays four dependent L2 round
+        // trips per row.  Same FMA order (even / odd accumulators in batches of 8, tail on a0): same bits.
+        double pv[32];
 #pragma unroll
-        for (int u = 0; u < 8; u++) pv[u] = Pi[(size_t)(t + u) * nf];
+        for (int u = 0; u < 32; u++) pv[u] = (u < w) ? Pi[(size_t)u * nf] : 0.0;
+        const int w8 = w & ~7;
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) { a0 = fma(-pv[u], fsh[k0 + t + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + t + u + 1], a1); }
+        for (int u = 0; u < 32; u += 2) {
+          if (u + 1 < w8) { a0 = fma(-pv[u], fsh[k0 + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + u + 1], a1); }
+        }
+#pragma unroll
+        for (int u = 0; u < 32; u++) if (u >= w8 && u < w) a0 = fma(-pv[u], fsh[k0 + u], a0);
+      } else {
+        int t = 0;
+        for (; t + 8 <= w; t += 8) {
+          double pv[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) pv[u] = Pi[(size_t)(t + u) * nf];
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) { a0 = fma(-pv[u], fsh[k0 + t + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + t + u + 1], a1); }
+        }
+        for (; t < w; t++) a0 = fma(-Pi[(size_t)t * nf], fsh[k0 + t], a0);
       }
-      for (; t < w; t++) a0 = fma(-Pi[(size_t)t * nf], fsh[k0 + t], a0);
       fsh[i] = a0 + a1;
     }
     __syncthreads();
@@ -831,17 +846,41 @@ __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restric
       if (r == c) { dgl[r] = e; e = 1.0 / e; }
       blk[r][c] = e;
     }
-    for (int t = warp; t < w; t += nw) {
-      const double *col = P + (size_t)(k0 + t) * nf;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int i = k0 + w + lane;
-      for (; i + 96 < nf; i += 128) {      // four independent loads in flight per lane
-        a0 = fma(col[i], fsh[i], a0); a1 = fma(col[i + 32], fsh[i + 32], a1);
-        a2 = fma(col[i + 64], fsh[i + 64], a2); a3 = fma(col[i + 96], fsh[i + 96], a3);
+    // A warp takes its (up to four with eight warps) columns TOGETHER: sixteen independent loads in flight per lane instead of four
+    // (one column after the other paid nf / 128 dependent L2 round trips per column).  Per column the accumulation order is unchanged.
+    for (int t0 = warp; t0 < w; t0 += 4 * nw) {
+      const double *col[4];
+      double a[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        col[c] = P + (size_t)(k0 + min(t0 + c * nw, w - 1)) * nf;
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[c][q] = 0.0;
       }
-      for (; i < nf; i += 32) a0 = fma(col[i], fsh[i], a0);
-      const double a = warp_sum((a0 + a1) + (a2 + a3));
-      if (lane == 0) fsh[k0 + t] -= a;
+      int i = k0 + w + lane;
+      for (; i + 96 < nf; i += 128) {
+        double v[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[c][q] = col[c][i + 32 * q];
+        const double f0 = fsh[i], f1 = fsh[i + 32], f2 = fsh[i + 64], f3 = fsh[i + 96];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          a[c][0] = fma(v[c][0], f0, a[c][0]); a[c][1] = fma(v[c][1], f1, a[c][1]);
+          a[c][2] = fma(v[c][2], f2, a[c][2]); a[c][3] = fma(v[c][3], f3, a[c][3]);
+        }
+      }
+      for (; i < nf; i += 32) {
+        const double f = fsh[i];
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[c][0] = fma(col[c][i], f, a[c][0]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double sacc = warp_sum((a[c][0] + a[c][1]) + (a[c][2] + a[c][3]));
+        if (lane == 0 && t0 + c * nw < w) fsh[k0 + t0 + c * nw] -= sacc;
+      }
     }
     __syncthreads();
     if (tid < 32) {
@@ -863,7 +902,8 @@ int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, con
   const int n = sc->d.n;
   static bool attr_set = false;
   if (!attr_set) {
-    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
@@ -873,7 +913,8 @@ int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, con
     const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
     if (cnt <= 0) continue;
     const int mnf = h.lvl_max_nf[l];
-    QB_LAUNCH(k_mf_fwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+    if (mnf <= 64) QB_LAUNCH(k_mf_fwd<false>, cnt, 64, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+    else QB_LAUNCH(k_mf_fwd<true>, cnt, 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
   }
   if (sc->d.sgn) QB_LAUNCH(k_sp_apply_sign, cdiv(n, 256), 256, 0, st, sc->d, sc->v);   // L S L' x = b: y <- inv(S) y = S y
   for (int l = h.nlevels - 1; l >= 0; l--) {

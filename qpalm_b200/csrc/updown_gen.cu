@@ -415,10 +415,19 @@ int chol_updown_gen(cudaStream_t s, int npad, double *L, int ld, const double *i
     if (st.tdump) QB_CUDA_TRY(cudaFree(st.tdump));
     st.packets = nullptr; st.buf = nullptr; st.tdump = nullptr; st.cap_npad = 0;
     const size_t nblk = (size_t)npad / NB, nblocks = (size_t)npad / GB;
-    QB_CUDA_TRY(cudaMalloc(&st.packets, sizeof(uint4) * (size_t)npad * 32));
+    // work space of a pass: 16 B x 32 per row of packets, 65 doubles per row of What | Z | D, the Gram prefixes and the running sums of
+    // every tile (n = 8000: 66 MB; n = 30 000: 0.9 GB).  If HBM cannot hold it the caller takes the dataflow sweep, which needs none.
+    const cudaError_t e1 = cudaMalloc(&st.packets, sizeof(uint4) * (size_t)npad * 32);
+    const cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&st.buf, sizeof(double) * ((size_t)npad * 65 + nblocks * 32 * 32)) : e1;
+    const cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc(&st.tdump, sizeof(double) * (nblk * (nblk + 1) / 2) * NB * 32) : e2;
+    if (e3 != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (st.packets) cudaFree(st.packets);
+      if (st.buf) cudaFree(st.buf);
+      st.packets = nullptr; st.buf = nullptr; st.tdump = nullptr;
+      return 1;
+    }
     QB_CUDA_TRY(cudaMemsetAsync(st.packets, 0, sizeof(uint4) * (size_t)npad * 32, s));
-    QB_CUDA_TRY(cudaMalloc(&st.buf, sizeof(double) * ((size_t)npad * 65 + nblocks * 32 * 32)));
-    QB_CUDA_TRY(cudaMalloc(&st.tdump, sizeof(double) * (nblk * (nblk + 1) / 2) * NB * 32));
     st.cap_npad = npad;
     st.epoch = 0;
   }
