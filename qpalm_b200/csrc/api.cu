@@ -399,6 +399,7 @@ static void boost_gamma(QPALMWorkspace *work) {   // iteration.c:159-211
 static bool prefer_updown(const Engine *e, int k) {
   if (k <= 0) return false;
   if (e->kkt) return false;   // KKT path: a changed row is rewritten and the system refactorised (kkt.cu)
+  if (e->updown_max_rank == 0) return false;   // QPALM_B200_UPDOWN_MAX_RANK=0: always refactorise, whatever the update path
   const bool flow = !e->sp && e->updown_flow_ok && e->npad >= 256;   // one-launch dataflow sweep, <= 64 ranks each (updown_flow.cu)
   const bool gen = use_updown_gen(e);                                // generator-form passes, <= 32 ranks each (updown_gen.cu)
   if (gen) {
