@@ -26,6 +26,7 @@
 // Every sum has a fixed order (no atomics): re-solves are bit-reproducible (tests/src/test_basic_qp.c:298-305).
 // The caller refreshes the inverses of the diagonal blocks afterwards (trtri_diag_blocks), as after the dataflow sweep.
 #include "dense.cuh"
+#include "chol32.cuh"
 #include <map>
 #include <mutex>
 
@@ -217,20 +218,36 @@ __global__ void __launch_bounds__(256) k_gen_gram(const double *__restrict__ Wha
   }
 }
 
-// in place: G[B] <- S + sum_{B' < B} G[B']   (S = diag(+1 x kpos, -1 x (k - kpos), +1 pad))
+// in place: G[B] <- S + sum_{B' < B} G[B']   (S = diag(+1 x kpos, -1 x (k - kpos), +1 pad)).  Two-level scan inside one CTA per 64
+// matrix entries: 16 threads per entry, each scans a contiguous chunk of blocks (its loads are independent and all in flight),
+// the chunk totals meet in shared memory.  (One thread per entry walking all npad / 32 blocks: 41 us at n = 8000.)  The
+// summation order is fixed by the chunking (chunk sums, then their prefix), so results are reproducible.
+constexpr int SCAN_E = 64, SCAN_C = 16;
 template <int KW>
-__global__ void __launch_bounds__(KW * KW) k_gen_scan(double *G, int nblocks, int k, int kpos) {
-  const int idx = threadIdx.x, a = idx / KW, b = idx - a * KW;
-  double run = (a == b) ? ((a < kpos || a >= k) ? 1.0 : -1.0) : 0.0;
-  int B = 0;
-  for (; B + 8 <= nblocks; B += 8) {
+__global__ void __launch_bounds__(SCAN_E * SCAN_C) k_gen_scan(double *G, int nblocks, int k, int kpos) {
+  __shared__ double tot[SCAN_C][SCAN_E + 1];
+  const int el = threadIdx.x % SCAN_E, ch = threadIdx.x / SCAN_E;
+  const int idx = (int)blockIdx.x * SCAN_E + el, a = idx / KW, b = idx - a * KW;
+  const int per = (nblocks + SCAN_C - 1) / SCAN_C, B0 = ch * per, B1 = min(nblocks, B0 + per);
+  double sum = 0.0;
+  for (int B = B0; B < B1; B += 8) {
     double v[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = G[(size_t)(B + u) * KW * KW + idx];
+    for (int u = 0; u < 8; u++) v[u] = (B + u < B1) ? G[(size_t)(B + u) * KW * KW + idx] : 0.0;
 #pragma unroll
-    for (int u = 0; u < 8; u++) { G[(size_t)(B + u) * KW * KW + idx] = run; run += v[u]; }
+    for (int u = 0; u < 8; u++) sum += v[u];
   }
-  for (; B < nblocks; B++) { const double v = G[(size_t)B * KW * KW + idx]; G[(size_t)B * KW * KW + idx] = run; run += v; }
+  tot[ch][el] = sum;
+  __syncthreads();
+  double run = (a == b) ? ((a < kpos || a >= k) ? 1.0 : -1.0) : 0.0;
+  for (int c = 0; c < ch; c++) run += tot[c][el];
+  for (int B = B0; B < B1; B += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = (B + u < B1) ? G[(size_t)(B + u) * KW * KW + idx] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (B + u < B1) { G[(size_t)(B + u) * KW * KW + idx] = run; run += v[u]; }
+  }
 }
 
 // one warp per 32-row block: P = inv(M_B) by Gauss-Jordan (lane = row, no pivoting: M_B is positive definite for an
@@ -275,7 +292,9 @@ __global__ void __launch_bounds__(32) k_gen_rows(const double *__restrict__ What
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const double d2 = 1.0 + s;
     if (!(d2 > 0.0)) bad = true;
-    const double d = sqrt(d2), z = g / d;
+    double d, rd;
+    chol32::sqrt_and_rcp(d2, d, rd);       // branch-free correctly rounded sqrt and its reciprocal (no slow-path calls on the chain)
+    const double z = g * rd;
 #pragma unroll
     for (int c = 0; c < KW; c++) p[c] = fma(-z, __shfl_sync(0xffffffffu, z, c), p[c]);
     const size_t row = (size_t)B * GB + jj;
@@ -388,7 +407,7 @@ static int run(cudaStream_t s, State &st, int slot, int npad, double *L, int ld,
     ++g_kernel_launches;
   }
   QB_LAUNCH(k_gen_gram<KT>, nblocks, 256, 0, s, What, npad, G);
-  QB_LAUNCH(k_gen_scan<KT>, 1, KT * KT, 0, s, G, nblocks, k, kpos);
+  QB_LAUNCH(k_gen_scan<KT>, KT * KT / SCAN_E, SCAN_E * SCAN_C, 0, s, G, nblocks, k, kpos);
   QB_LAUNCH(k_gen_rows<KT>, nblocks, 32, 0, s, What, npad, G, D, Z, info_dev);
   const int ntile = nblk * (nblk + 1) / 2;
   QB_LAUNCH(k_gen_apply<KT>, ntile, NB, ApplySmem<KT>::bytes, s, L, ld, W, ldw, k, What, Z, D, npad, st.tdump);
