@@ -755,7 +755,6 @@ __device__ __forceinline__ double div_by_rcp(double x, double l, double r) {
   return fma(fma(-q, l, x), r, q);
 }
 
-template <bool BIG>   // BIG: levels with fronts above 64 rows (256 threads); the leaf levels keep the small-register loop
 __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restrict__ panels, double *v, double *uvec, int lvl_begin) {
   extern __shared__ double fsh[];
   __shared__ double blk[32][33];
@@ -792,37 +791,113 @@ __global__ void __launch_bounds__(256) k_mf_fwd(SpDev d, const double *__restric
     }
     __syncthreads();
     for (int i = k0 + w + tid; i < nf; i += blockDim.x) {
+      // 8 independent loads in flight per thread (a rolled loop pays one L2 round trip per column)
       const double *Pi = P + (size_t)i + (size_t)k0 * nf;
       double a0 = fsh[i], a1 = 0.0;
-      if constexpr (BIG) {
-        // all (<= 32) loads of the row in flight at once: the rolled loop of 8-column batches below pays four dependent L2 round
-        // trips per row.  Same FMA order (even / odd accumulators in batches of 8, tail on a0): same bits.
-        double pv[32];
+      int t = 0;
+      for (; t + 8 <= w; t += 8) {
+        double pv[8];
 #pragma unroll
-        for (int u = 0; u < 32; u++) pv[u] = (u < w) ? Pi[(size_t)u * nf] : 0.0;
-        const int w8 = w & ~7;
+        for (int u = 0; u < 8; u++) pv[u] = Pi[(size_t)(t + u) * nf];
 #pragma unroll
-        for (int u = 0; u < 32; u += 2) {
-          if (u + 1 < w8) { a0 = fma(-pv[u], fsh[k0 + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + u + 1], a1); }
-        }
-#pragma unroll
-        for (int u = 0; u < 32; u++) if (u >= w8 && u < w) a0 = fma(-pv[u], fsh[k0 + u], a0);
-      } else {
-        int t = 0;
-        for (; t + 8 <= w; t += 8) {
-          double pv[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) pv[u] = Pi[(size_t)(t + u) * nf];
-#pragma unroll
-          for (int u = 0; u < 8; u += 2) { a0 = fma(-pv[u], fsh[k0 + t + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + t + u + 1], a1); }
-        }
-        for (; t < w; t++) a0 = fma(-Pi[(size_t)t * nf], fsh[k0 + t], a0);
+        for (int u = 0; u < 8; u += 2) { a0 = fma(-pv[u], fsh[k0 + t + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + t + u + 1], a1); }
       }
+      for (; t < w; t++) a0 = fma(-Pi[(size_t)t * nf], fsh[k0 + t], a0);
       fsh[i] = a0 + a1;
     }
     __syncthreads();
   }
   for (int i = tid; i < nf; i += blockDim.x) { if (i < ns) v[f + i] = fsh[i]; else uvec[ro + i - ns] = fsh[i]; }
+}
+
+// The same forward step for the levels of LARGE fronts (few CTAs, each streaming a panel of up to a few MB): only the
+// right-hand side carries a dependence from block to block, the factor does not -- so every load of the factor is issued
+// ahead of the step that needs it.  Per 32-column block: the values of this thread's first row below the block are requested
+// BEFORE the one-warp substitution on the diagonal block and consumed after it, the next diagonal block travels through two
+// registers per thread and is written to shared memory while the row update runs.  512 threads, so most steps have one row
+// per thread.  (The generic kernel above paid, per block, one dependent L2 / HBM round trip for the diagonal block and two or
+// three for the rows: 9-14 us per block at the top of the assembly tree against 4 us for the backward step.)  The arithmetic
+// of every entry is that of the generic kernel, in the same order: identical bits.
+constexpr int kFwdBigThreads = 512;
+__global__ void __launch_bounds__(kFwdBigThreads) k_mf_fwd_big(SpDev d, const double *__restrict__ panels, double *v, double *uvec, int lvl_begin) {
+  extern __shared__ double fsh[];
+  __shared__ double blk[32][33];
+  __shared__ double dgl[32];
+  constexpr int NTB = kFwdBigThreads;
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+  const double *P = panels + d.panel_off[s];
+  const int tid = threadIdx.x;
+  // element t (of 1024) of the 32 x 32 diagonal block at k0n, as the generic kernel loads it
+  auto diag_elem = [&](int k0n, int t) -> double {
+    const int r = t & 31, c = t >> 5, wn = min(32, ns - k0n);
+    return (r < wn && c <= r) ? P[(size_t)(k0n + r) + (size_t)(k0n + c) * nf] : ((r == c) ? 1.0 : 0.0);
+  };
+  auto diag_store = [&](int t, double e) {
+    const int r = t & 31, c = t >> 5;
+    if (r == c) { dgl[r] = e; e = 1.0 / e; }
+    blk[r][c] = e;
+  };
+  double nb0 = diag_elem(0, tid), nb1 = diag_elem(0, tid + NTB);      // in flight during the prologue
+  for (int i = tid; i < nf; i += NTB) fsh[i] = (i < ns) ? v[f + i] : 0.0;
+  __syncthreads();
+  for (int ch = d.child_ptr[s]; ch < d.child_ptr[s + 1]; ch++) {
+    const int c = d.child_idx[ch];
+    const int cro = d.rows_off[c], cnr = d.rows_off[c + 1] - cro;
+    for (int i = tid; i < cnr; i += NTB) fsh[d.rel[cro + i]] += uvec[cro + i];
+    __syncthreads();
+  }
+  diag_store(tid, nb0); diag_store(tid + NTB, nb1);
+  __syncthreads();
+  for (int k0 = 0; k0 < ns; k0 += 32) {
+    const int w = min(32, ns - k0), w8 = w & ~7;
+    // requests that do not wait for the substitution below: this thread's first row under the block, the next diagonal block
+    const int i1 = k0 + w + tid;
+    double pv[32];
+    {
+      const double *Pi = P + (size_t)i1 + (size_t)k0 * nf;
+#pragma unroll
+      for (int u = 0; u < 32; u++) pv[u] = (i1 < nf && u < w) ? Pi[(size_t)u * nf] : 0.0;
+    }
+    const bool more = k0 + 32 < ns;
+    if (more) { nb0 = diag_elem(k0 + 32, tid); nb1 = diag_elem(k0 + 32, tid + NTB); }
+    if (tid < 32) {
+      double x = (tid < w) ? fsh[k0 + tid] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const double xj = div_by_rcp(__shfl_sync(0xffffffffu, x, j), dgl[j], blk[j][j]);
+        if (tid == j) x = xj; else if (tid > j) x = fma(-blk[tid][j], xj, x);
+      }
+      if (tid < w) fsh[k0 + tid] = x;
+    }
+    __syncthreads();
+    if (i1 < nf) {
+      double a0 = fsh[i1], a1 = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32; u += 2) {
+        if (u + 1 < w8) { a0 = fma(-pv[u], fsh[k0 + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + u + 1], a1); }
+      }
+#pragma unroll
+      for (int u = 0; u < 32; u++) if (u >= w8 && u < w) a0 = fma(-pv[u], fsh[k0 + u], a0);
+      fsh[i1] = a0 + a1;
+    }
+    for (int i = i1 + NTB; i < nf; i += NTB) {      // fronts of more than 512 + 32 rows: the remaining rows
+      const double *Pi = P + (size_t)i + (size_t)k0 * nf;
+#pragma unroll
+      for (int u = 0; u < 32; u++) pv[u] = (u < w) ? Pi[(size_t)u * nf] : 0.0;
+      double a0 = fsh[i], a1 = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32; u += 2) {
+        if (u + 1 < w8) { a0 = fma(-pv[u], fsh[k0 + u], a0); a1 = fma(-pv[u + 1], fsh[k0 + u + 1], a1); }
+      }
+#pragma unroll
+      for (int u = 0; u < 32; u++) if (u >= w8 && u < w) a0 = fma(-pv[u], fsh[k0 + u], a0);
+      fsh[i] = a0 + a1;
+    }
+    if (more) { diag_store(tid, nb0); diag_store(tid + NTB, nb1); }     // blk / dgl are free: the substitution ended before the barrier
+    __syncthreads();
+  }
+  for (int i = tid; i < nf; i += NTB) { if (i < ns) v[f + i] = fsh[i]; else uvec[ro + i - ns] = fsh[i]; }
 }
 
 // backward: L' x = y.  f = [y_s ; x(R_s)]; per 32-column block (descending): subtract the column dots with everything
@@ -897,31 +972,51 @@ __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restric
   for (int i = tid; i < ns; i += blockDim.x) v[f + i] = fsh[i];
 }
 
+// QPALM_B200_MF_LEVEL_NAMES=1: the profiler (prof.cu) sees the solve launches under per-level names ("k_mf_fwd.L17")
+static bool level_names() { static const bool on = getenv("QPALM_B200_MF_LEVEL_NAMES") != nullptr; return on; }
+static const char *level_name(const char *base, int l) {
+  static char names[2][64][24];
+  static bool init = false;
+  if (!init) {
+    for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) snprintf(names[k][i], sizeof(names[k][i]), "%s.L%02d", k == 0 ? "k_mf_fwd" : "k_mf_bwd", i);
+    init = true;
+  }
+  return names[base[5] == 'f' ? 0 : 1][l < 63 ? l : 63];
+}
+
 int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, const double *rhs, double *out, bool negate) {
   const SymHost &h = sc->h;
   const int n = sc->d.n;
   static bool attr_set = false;
   if (!attr_set) {
-    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (sizeof(double) * (size_t)h.max_nf > 200 * 1024) { fprintf(stderr, "[qpalm_b200] sparse solve: front of %d rows exceeds the shared-memory vector\n", h.max_nf); return 4; }
+  const char *fg = getenv("QPALM_B200_MF_FWD_GENERIC");     // tests: the generic forward kernel on every level (bit-identity check)
+  const bool fwd_generic = fg && atoi(fg) != 0;
   QB_LAUNCH(k_sp_permute_in, cdiv(n, 256), 256, 0, st, sc->d, rhs, sc->v, negate ? -1.0 : 1.0);
   for (int l = 0; l < h.nlevels; l++) {
     const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
     if (cnt <= 0) continue;
     const int mnf = h.lvl_max_nf[l];
-    if (mnf <= 64) QB_LAUNCH(k_mf_fwd<false>, cnt, 64, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
-    else QB_LAUNCH(k_mf_fwd<true>, cnt, 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+    const bool lp = g_prof_on && level_names() && prof_begin(level_name("k_mf_fwd", l), st);   // per-level timing (diagnostics)
+    const int po = g_prof_on; if (lp) g_prof_on = 0;
+    if (mnf > kSmallMaxNf && !fwd_generic) QB_LAUNCH(k_mf_fwd_big, cnt, kFwdBigThreads, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+    else QB_LAUNCH(k_mf_fwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, sc->uvec, b);
+    if (lp) { g_prof_on = po; prof_end(st); }
   }
   if (sc->d.sgn) QB_LAUNCH(k_sp_apply_sign, cdiv(n, 256), 256, 0, st, sc->d, sc->v);   // L S L' x = b: y <- inv(S) y = S y
   for (int l = h.nlevels - 1; l >= 0; l--) {
     const int b = h.lvl_ptr[l], cnt = h.lvl_ptr[l + 1] - b;
     if (cnt <= 0) continue;
     const int mnf = h.lvl_max_nf[l];
+    const bool lp = g_prof_on && level_names() && prof_begin(level_name("k_mf_bwd", l), st);
+    const int po = g_prof_on; if (lp) g_prof_on = 0;
     QB_LAUNCH(k_mf_bwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, b);
+    if (lp) { g_prof_on = po; prof_end(st); }
   }
   QB_LAUNCH(k_sp_permute_out, cdiv(n, 256), 256, 0, st, sc->d, sc->v, out);
   QB_CUDA_TRY(cudaGetLastError());

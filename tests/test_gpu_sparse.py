@@ -90,6 +90,28 @@ def test_cluster_front_kernel_equals_per_block_launches(name, make, cluster):
     assert np.max(np.abs(out["cluster"][0] - dref)) <= 1e-9 * max(1.0, np.max(np.abs(dref)))
 
 
+@pytest.mark.parametrize("name,make", [("grid70", lambda: problems.grid_qp(70, seed=6)),
+                                       ("rand_one_front_700", lambda: problems.random_qp(700, 900, 0.2, 0.1, seed=5))],
+                         ids=["grid70", "rand_one_front_700"])
+def test_pipelined_forward_solve_equals_generic_kernel(name, make):
+    """Levels of large fronts take k_mf_fwd_big (factor loads issued ahead of the substitution, 512 threads); the generic kernel stays
+    behind QPALM_B200_MF_FWD_GENERIC=1.  Same arithmetic per entry in the same order: the solutions must be bit-identical."""
+    p = make()
+    rng = np.random.default_rng(33)
+    sigma = 0.5 + 20 * rng.random(p.m); act = (rng.random(p.m) < 0.5).astype(np.int64); rhs = rng.standard_normal(p.n)
+    out = {}
+    for mode, flag in (("generic", "1"), ("pipelined", "0")):
+        old = os.environ.get("QPALM_B200_MF_FWD_GENERIC")
+        os.environ["QPALM_B200_MF_FWD_GENERIC"] = flag
+        try:
+            out[mode] = sparse_newton(p.Q, p.A, sigma, act, 1e-3, rhs)[0]
+        finally:
+            os.environ.pop("QPALM_B200_MF_FWD_GENERIC", None) if old is None else os.environ.__setitem__("QPALM_B200_MF_FWD_GENERIC", old)
+    assert np.array_equal(out["generic"], out["pipelined"])
+    dref = np.linalg.solve(_dense_H(p, sigma, act, 1e-3), rhs)
+    assert np.max(np.abs(out["pipelined"] - dref)) <= 1e-9 * max(1.0, np.max(np.abs(dref)))
+
+
 @pytest.mark.parametrize("name,make", [("grid31", lambda: problems.grid_qp(31, seed=2)),
                                        ("rand_sparse", lambda: problems.random_qp(150, 260, 0.02, 0.01, seed=3)),
                                        ("grid70", lambda: problems.grid_qp(70, seed=6))], ids=["grid31", "rand_sparse", "grid70"])
