@@ -972,6 +972,128 @@ __global__ void __launch_bounds__(256) k_mf_bwd(SpDev d, const double *__restric
   for (int i = tid; i < ns; i += blockDim.x) v[f + i] = fsh[i];
 }
 
+// The backward step for the levels of LARGE fronts, with the factor loads issued ahead as in k_mf_fwd_big: while warp 0 runs the
+// substitution of block kb, every warp already holds the requests for block kb - 1 -- its diagonal block (two registers per
+// thread) and the first 256 rows of its two columns' dots (sixteen registers per lane).  512 threads = 16 warps, two columns
+// per warp.  Per column the accumulation order is that of k_mf_bwd (four accumulators over 128-row strides, tail on the
+// first): identical bits.
+constexpr int kBwdBigThreads = 512;
+__global__ void __launch_bounds__(kBwdBigThreads) k_mf_bwd_big(SpDev d, const double *__restrict__ panels, double *v, int lvl_begin) {
+  extern __shared__ double fsh[];
+  __shared__ double blk[32][33];
+  __shared__ double dgl[32];
+  constexpr int NTB = kBwdBigThreads, NWB = NTB / 32;
+  const int s = d.lvl_sn[lvl_begin + blockIdx.x];
+  const int f = d.first[s], ns = d.first[s + 1] - f, ro = d.rows_off[s], nr = d.rows_off[s + 1] - ro, nf = ns + nr;
+  const double *P = panels + d.panel_off[s];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double nb0, nb1, pre[2][8];
+  auto prefetch = [&](int kb) {
+    const int k0 = kb * 32, w = min(32, ns - k0), i0 = k0 + w + lane;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int t = tid + e * NTB, r = t & 31, c = t >> 5;
+      const double x = (r < w && c <= r) ? P[(size_t)(k0 + r) + (size_t)(k0 + c) * nf] : ((r == c) ? 1.0 : 0.0);
+      if (e == 0) nb0 = x; else nb1 = x;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const double *col = P + (size_t)(k0 + min(warp + c * NWB, w - 1)) * nf;
+#pragma unroll
+      for (int m = 0; m < 8; m++) pre[c][m] = (i0 + 32 * m < nf) ? col[i0 + 32 * m] : 0.0;
+    }
+  };
+  const int nb = (ns + 31) / 32;
+  prefetch(nb - 1);
+  for (int i = tid; i < nf; i += NTB) fsh[i] = (i < ns) ? v[f + i] : v[d.rowidx[ro + i - ns]];
+  __syncthreads();
+  for (int kb = nb - 1; kb >= 0; kb--) {
+    const int k0 = kb * 32, w = min(32, ns - k0);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int t = tid + e * NTB, r = t & 31, c = t >> 5;
+      double x = e == 0 ? nb0 : nb1;
+      if (r == c) { dgl[r] = x; x = 1.0 / x; }
+      blk[r][c] = x;
+    }
+    {
+      const int i0 = k0 + w + lane;
+      const int nfull = (nf - i0 - 96 > 0) ? (nf - i0 - 96 + 127) / 128 : 0;
+      const double *col[2];
+      double a[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        col[c] = P + (size_t)(k0 + min(warp + c * NWB, w - 1)) * nf;
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[c][q] = 0.0;
+      }
+#pragma unroll
+      for (int it = 0; it < 2; it++) {
+        if (it < nfull) {
+          const int i = i0 + 128 * it;
+          const double f0 = fsh[i], f1 = fsh[i + 32], f2 = fsh[i + 64], f3 = fsh[i + 96];
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            a[c][0] = fma(pre[c][4 * it], f0, a[c][0]); a[c][1] = fma(pre[c][4 * it + 1], f1, a[c][1]);
+            a[c][2] = fma(pre[c][4 * it + 2], f2, a[c][2]); a[c][3] = fma(pre[c][4 * it + 3], f3, a[c][3]);
+          }
+        }
+      }
+      for (int it = 2; it < nfull; it++) {
+        const int i = i0 + 128 * it;
+        double vv[2][4];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) vv[c][q] = col[c][i + 32 * q];
+        const double f0 = fsh[i], f1 = fsh[i + 32], f2 = fsh[i + 64], f3 = fsh[i + 96];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          a[c][0] = fma(vv[c][0], f0, a[c][0]); a[c][1] = fma(vv[c][1], f1, a[c][1]);
+          a[c][2] = fma(vv[c][2], f2, a[c][2]); a[c][3] = fma(vv[c][3], f3, a[c][3]);
+        }
+      }
+      // tail (at most three rows per lane), on the first accumulator
+      if (nfull == 0) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const int i = i0 + 32 * m;
+          if (i < nf) { const double fv = fsh[i]; a[0][0] = fma(pre[0][m], fv, a[0][0]); a[1][0] = fma(pre[1][m], fv, a[1][0]); }
+        }
+      } else if (nfull == 1) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const int i = i0 + 128 + 32 * m;
+          if (i < nf) { const double fv = fsh[i]; a[0][0] = fma(pre[0][4 + m], fv, a[0][0]); a[1][0] = fma(pre[1][4 + m], fv, a[1][0]); }
+        }
+      } else {
+        for (int i = i0 + 128 * nfull; i < nf; i += 32) {
+          const double fv = fsh[i];
+          a[0][0] = fma(col[0][i], fv, a[0][0]); a[1][0] = fma(col[1][i], fv, a[1][0]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const double sacc = warp_sum((a[c][0] + a[c][1]) + (a[c][2] + a[c][3]));
+        if (lane == 0 && warp + c * NWB < w) fsh[k0 + warp + c * NWB] -= sacc;
+      }
+    }
+    __syncthreads();
+    if (kb > 0) prefetch(kb - 1);      // in flight during the substitution below
+    if (tid < 32) {
+      double x = (tid < w) ? fsh[k0 + tid] : 0.0;
+#pragma unroll
+      for (int j = 31; j >= 0; j--) {
+        const double xj = div_by_rcp(__shfl_sync(0xffffffffu, x, j), dgl[j], blk[j][j]);
+        if (tid == j) x = xj; else if (tid < j) x = fma(-blk[j][tid], xj, x);
+      }
+      if (tid < w) fsh[k0 + tid] = x;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < ns; i += NTB) v[f + i] = fsh[i];
+}
+
 // QPALM_B200_MF_LEVEL_NAMES=1: the profiler (prof.cu) sees the solve launches under per-level names ("k_mf_fwd.L17")
 static bool level_names() { static const bool on = getenv("QPALM_B200_MF_LEVEL_NAMES") != nullptr; return on; }
 static const char *level_name(const char *base, int l) {
@@ -992,10 +1114,11 @@ int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, con
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_fwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_TRY(cudaFuncSetAttribute(k_mf_bwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (sizeof(double) * (size_t)h.max_nf > 200 * 1024) { fprintf(stderr, "[qpalm_b200] sparse solve: front of %d rows exceeds the shared-memory vector\n", h.max_nf); return 4; }
-  const char *fg = getenv("QPALM_B200_MF_FWD_GENERIC");     // tests: the generic forward kernel on every level (bit-identity check)
+  const char *fg = getenv("QPALM_B200_MF_FWD_GENERIC");     // tests: the generic forward / backward kernels on every level (bit-identity check)
   const bool fwd_generic = fg && atoi(fg) != 0;
   QB_LAUNCH(k_sp_permute_in, cdiv(n, 256), 256, 0, st, sc->d, rhs, sc->v, negate ? -1.0 : 1.0);
   for (int l = 0; l < h.nlevels; l++) {
@@ -1015,7 +1138,8 @@ int sparse_chol_solve(SparseChol *sc, cudaStream_t st, const double *panels, con
     const int mnf = h.lvl_max_nf[l];
     const bool lp = g_prof_on && level_names() && prof_begin(level_name("k_mf_bwd", l), st);
     const int po = g_prof_on; if (lp) g_prof_on = 0;
-    QB_LAUNCH(k_mf_bwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, b);
+    if (mnf > kSmallMaxNf && !fwd_generic) QB_LAUNCH(k_mf_bwd_big, cnt, kBwdBigThreads, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, b);
+    else QB_LAUNCH(k_mf_bwd, cnt, mnf <= 64 ? 64 : 256, sizeof(double) * (size_t)mnf, st, sc->d, panels, sc->v, b);
     if (lp) { g_prof_on = po; prof_end(st); }
   }
   QB_LAUNCH(k_sp_permute_out, cdiv(n, 256), 256, 0, st, sc->d, sc->v, out);

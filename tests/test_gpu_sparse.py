@@ -93,8 +93,8 @@ def test_cluster_front_kernel_equals_per_block_launches(name, make, cluster):
 @pytest.mark.parametrize("name,make", [("grid70", lambda: problems.grid_qp(70, seed=6)),
                                        ("rand_one_front_700", lambda: problems.random_qp(700, 900, 0.2, 0.1, seed=5))],
                          ids=["grid70", "rand_one_front_700"])
-def test_pipelined_forward_solve_equals_generic_kernel(name, make):
-    """Levels of large fronts take k_mf_fwd_big (factor loads issued ahead of the substitution, 512 threads); the generic kernel stays
+def test_pipelined_solves_equal_generic_kernels(name, make):
+    """Levels of large fronts take k_mf_fwd_big / k_mf_bwd_big (factor loads issued ahead of the substitution, 512 threads); the generic kernels stay
     behind QPALM_B200_MF_FWD_GENERIC=1.  Same arithmetic per entry in the same order: the solutions must be bit-identical."""
     p = make()
     rng = np.random.default_rng(33)
