@@ -5,14 +5,20 @@
 // lower triangle used.  "Front" index space of s: 0..ns-1 = own columns, ns..nf-1 = R_s.
 //
 // Numeric factorization, level l (all supernodes whose children are done):
-//   k_mf_extend   U_s <- 0, then panel_s / U_s += U_c scattered through rel_c for every child c (fixed order; each
-//                 CTA owns a range of target columns => no atomics, bit-reproducible)
-//   per 32-column block kb of the panel:   k_mf_diag (32 x 32 Cholesky in registers, one warp per front),
-//                 k_mf_trsm (rows below the block, one thread per row), k_mf_syrk (trailing update of the rest of the
-//                 panel and of U_s, 64 x 64 tiles, 4 x 4 per thread)
-//   levels whose fronts all fit in shared memory take k_mf_small instead: ONE launch does extend-add + partial
-//   factorization + write-back with the whole front resident in shared memory.
-// Solves: k_mf_fwd / k_mf_bwd, one CTA per supernode per level, per-supernode update vectors (pull-based).
+//   levels whose fronts all fit in shared memory: k_mf_small, ONE launch does extend-add + partial factorization +
+//                 write-back with the whole front resident in shared memory.
+//   larger fronts: mfc::k_mf_front, ONE launch per level with a thread-block CLUSTER per front (extend-add over all warps
+//                 of the cluster, then per 32 columns: rows below the block, cluster barrier, trailing 64 x 64 tiles while
+//                 the chain CTA factors the next diagonal block in registers, cluster barrier).
+//   The per-block launches the cluster kernel replaced stay behind QPALM_B200_MF_PER_BLOCK=1 (and as the fallback when a
+//   cluster launch is refused): k_mf_extend (U_s <- 0, then panel_s / U_s += U_c scattered through rel_c for every child c in
+//   a fixed order, each CTA owning a range of target columns => no atomics, bit-reproducible), then per 32-column block
+//   k_mf_diag (32 x 32 Cholesky in registers, one warp per front), k_mf_trsm (rows below, one thread per row), k_mf_syrk
+//   (trailing update of the rest of the panel and of U_s, 64 x 64 tiles, 4 x 4 per thread).  Same operations in the same
+//   order: bit-identical factors.
+// Solves: one CTA per supernode per level, per-supernode update vectors (pull-based): k_mf_fwd / k_mf_bwd, and for the levels
+// of large fronts k_mf_fwd_big / k_mf_bwd_big, which issue every load of the (constant) factor ahead of the step that needs
+// it -- only the right-hand side carries a dependence from block to block.
 // Rank-k update/downdate: k_ud_mark marks the etree paths, k_ud_sweep walks them (one CTA, columns in ascending order).
 #include "sparse.cuh"
 #include "sparse_host.h"
