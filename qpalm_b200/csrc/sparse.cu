@@ -427,6 +427,8 @@ constexpr int NT = 256;
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cta_count() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
@@ -535,9 +537,27 @@ __global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double
     }
     __syncthreads();
     MF_CLK(3, 0);
-    // (b) rows below: X <- X inv(L11') inv(S); 32-row chunks round-robin over the warps of the cluster, lane = row
+    // (b) rows below: X <- X inv(L11') inv(S); 32-row chunks round-robin over the warps of the cluster, lane = row.
+    // The first chunk -- the rows of the NEXT diagonal block -- is warp 0 of the chain CTA's: it keeps a copy in shared memory
+    // (the slab), so the chain CTA starts the look-ahead from its own data without waiting for the other CTAs' rows.
+    const bool lookahead = cn > 1 && base < ns;   // the chain CTA owns the next diagonal block
+    const bool chain_ahead = lookahead && cr == 0;
+    const int wn = min(32, ns - base);
+    double dold[4];
+    if (chain_ahead) {                             // old values of the next diagonal block (final since the previous barrier)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int c = warp + 8 * q;
+        dold[q] = (lane < wn && c <= lane) ? __ldcg(P + (size_t)(base + lane) + (size_t)(base + c) * nf) : 0.0;
+      }
+    }
     for (int i0 = base + (cr * NW + warp) * 32; i0 < nf; i0 += cn * NW * 32) {
       const int i = i0 + lane;
+      const bool slab = chain_ahead && i0 == base;          // (cr == 0, warp == 0, first chunk)
+      if (slab && i >= nf) {
+#pragma unroll
+        for (int t = 0; t < 32; t++) sm.c.Sl[t][lane] = 0.0;
+      }
       if (i < nf) {
         double x[32];
 #pragma unroll
@@ -552,38 +572,31 @@ __global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double
         }
 #pragma unroll
         for (int t = 0; t < 32; t++) if (t < w) P[(size_t)i + (size_t)(k0 + t) * nf] = x[t];
+        if (slab) {                                          // Sl[c][r] = P(base + r, k0 + c), r < wn
+#pragma unroll
+          for (int t = 0; t < 32; t++) sm.c.Sl[t][lane] = (t < w && lane < wn) ? x[t] : 0.0;
+        }
       }
     }
     MF_CLK(4, 0);
-    cluster_sync();
+    if (chain_ahead) cluster_arrive(); else cluster_sync();          // the chain CTA completes this barrier after its look-ahead
     MF_CLK(5, 0);
     if (clk_on && tid == 0 && cr == 1) t_last = clock64();
     // (c) trailing update F(i, j) -= sum_t P(i, k0 + t) s_t P(j, k0 + t), i >= j >= base
-    const bool lookahead = cn > 1 && base < ns;   // the chain CTA owns the next diagonal block
     if (cn > 1 && cr == 0) {
       if (lookahead) {
-        const int wn = min(32, ns - base);
-        for (int t = tid; t < 32 * 32; t += NT) {
-          const int r = t & 31, c = t >> 5;        // Sl[c][r] = P(base + r, k0 + c)
-          sm.c.Sl[c][r] = (c < w && r < wn) ? __ldcg(P + (size_t)(base + r) + (size_t)(k0 + c) * nf) : 0.0;
-        }
-        double old[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int c = warp + 8 * q;
-          old[q] = (lane < wn && c <= lane) ? __ldcg(P + (size_t)(base + lane) + (size_t)(base + c) * nf) : 0.0;
-        }
-        __syncthreads();
+        __syncthreads();                                     // the slab (warp 0) is visible to the CTA
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int c = warp + 8 * q;
           double acc = 0.0;
 #pragma unroll 8
           for (int t = 0; t < 32; t++) acc = fma(sm.c.Sl[t][lane], sgn_of(d, F.f + k0 + min(t, w - 1)) * sm.c.Sl[t][c], acc);
-          sm.c.Dn[lane][c] = old[q] - acc;
+          sm.c.Dn[lane][c] = dold[q] - acc;
         }
         __syncthreads();
         if (warp == 0) factor_block(d, P + (size_t)base + (size_t)base * nf, nf, wn, F.f + base, sm.c.Dn, info);
+        cluster_wait();
       }
     } else {
       const int T = (nf - base + 63) / 64, ntile = T * (T + 1) / 2;
@@ -601,14 +614,22 @@ __global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double
           sm.t.As[c][r] = (c < w && i0 + r < nf) ? __ldcg(P + (size_t)(i0 + r) + (size_t)(k0 + c) * nf) : 0.0;
           sm.t.Bs[c][r] = (c < w && j0 + r < nf) ? sgn_of(d, F.f + k0 + c) * __ldcg(P + (size_t)(j0 + r) + (size_t)(k0 + c) * nf) : 0.0;
         }
-        // old values of the tile requested before the products
+        // old values of the tile requested before the products.  One base pointer per tile column (entry (i, j) = colp[b] + i, in
+        // the panel for j < ns, in the update block beyond): the per-entry address selection of front_at() -- two 64-bit
+        // multiplies and a branch for each of the 32 accesses of a thread -- was a quarter of a tile's instructions.
+        double *colp[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int j = j0 + ty + 16 * b;
+          colp[b] = (j < ns) ? F.P + (size_t)j * nf : F.U + (size_t)(j - ns) * F.nr - ns;
+        }
         double old[4][4];
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
           for (int a = 0; a < 4; a++) {
             const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
-            old[a][b] = (i < nf && j < nf && i >= j) ? __ldcg(front_at(F, i, j)) : 0.0;
+            old[a][b] = (i < nf && j < nf && i >= j) ? __ldcg(colp[b] + i) : 0.0;
           }
         __syncthreads();
         double acc[4][4];
@@ -634,8 +655,8 @@ __global__ void __launch_bounds__(NT) k_mf_front(SpDev d, double *panels, double
           for (int a = 0; a < 4; a++) {
             const int i = i0 + tx + 16 * a;
             if (i >= nf || i < j) continue;
-            if (lookahead && i < base + min(32, ns - base)) continue;      // the chain CTA writes the next diagonal block
-            *front_at(F, i, j) = old[a][b] - acc[a][b];
+            if (lookahead && i < base + wn) continue;      // the chain CTA writes the next diagonal block
+            colp[b][i] = old[a][b] - acc[a][b];
           }
         }
       }
